@@ -1,0 +1,706 @@
+// hanamaru_host.cpp -- host-side mirror of the reference (see hanamaru_host.h).
+// Scene authoring, OBJ parsing, BVH build and flattening.  Nothing here is on
+// the hot path and nothing here touches CUDA.
+#include "hanamaru_host.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+namespace hanamaru {
+
+hnm_config config::to_abi() {
+    hnm_config c;
+    memset(&c, 0, sizeof(c));
+    c.eps = EPS; c.offset = OFFSET; c.inf = INF; c.gamma_factor = GAMMA_FACTOR;
+    c.tone_exposure = TONE_MAPPING_EXPOSURE; c.tone_white_point = TONE_MAPPING_WHITE_POINT;
+    c.bilateral_sigma_i = BILATERAL_FILTER_SIGMA_I; c.bilateral_sigma_s = BILATERAL_FILTER_SIGMA_S;
+    c.supersampling = SUPERSAMPLING; c.bounce_limit = PATHTRACING_BOUNCE_LIMIT;
+    c.tone_mapping_mode = TONE_MAPPING_MODE; c.bilateral_iteration = BILATERAL_FILTER_ITERATION;
+    c.bilateral_diameter = BILATERAL_FILTER_DIAMETER;
+    return c;
+}
+
+// ---- src/color.rs:51-61 --------------------------------------------------------
+static double saturate(double v) { return std::fmin(std::fmax(v, 0.0), 1.0); }
+static Color hue(double h) {
+    return Color(saturate(std::fabs(h * 6.0 - 3.0) - 1.0), saturate(2.0 - std::fabs(h * 6.0 - 2.0)),
+                 saturate(2.0 - std::fabs(h * 6.0 - 4.0)));
+}
+Color hsv_to_rgb(Color c) { return ((hue(c.x) - 1.0) * c.y + 1.0) * c.z; }
+
+// ---- src/matrix.rs ---------------------------------------------------------------
+Matrix44 Matrix44::identity() {
+    Matrix44 m;
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) m.e[i][j] = (i == j) ? 1.0 : 0.0;
+    return m;
+}
+Matrix44 Matrix44::scale(double sx, double sy, double sz) {
+    Matrix44 m = identity();
+    m.e[0][0] = sx; m.e[1][1] = sy; m.e[2][2] = sz;
+    return m;
+}
+Matrix44 Matrix44::rotate_x(double t) {
+    double s = std::sin(t), c = std::cos(t);
+    Matrix44 m = identity();
+    m.e[1][1] = c; m.e[1][2] = -s; m.e[2][1] = s; m.e[2][2] = c;
+    return m;
+}
+Matrix44 Matrix44::rotate_y(double t) {
+    double s = std::sin(t), c = std::cos(t);
+    Matrix44 m = identity();
+    m.e[0][0] = c; m.e[0][2] = s; m.e[2][0] = -s; m.e[2][2] = c;
+    return m;
+}
+Matrix44 Matrix44::rotate_z(double t) {
+    double s = std::sin(t), c = std::cos(t);
+    Matrix44 m = identity();
+    m.e[0][0] = c; m.e[0][1] = -s; m.e[1][0] = s; m.e[1][1] = c;
+    return m;
+}
+Matrix44 Matrix44::translate(double tx, double ty, double tz) {
+    Matrix44 m = identity();
+    m.e[0][3] = tx; m.e[1][3] = ty; m.e[2][3] = tz;
+    return m;
+}
+Matrix44 Matrix44::operator*(const Matrix44& o) const {  // src/matrix.rs:163-176
+    Matrix44 r = identity();
+    for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++)
+            r.e[i][j] = e[i][0] * o.e[0][j] + e[i][1] * o.e[1][j] + e[i][2] * o.e[2][j] + e[i][3] * o.e[3][j];
+    return r;
+}
+Vector3 Matrix44::operator*(const Vector3& v) const {  // src/matrix.rs:180-190
+    return Vector3(v.x * e[0][0] + v.y * e[0][1] + v.z * e[0][2] + e[0][3],
+                   v.x * e[1][0] + v.y * e[1][1] + v.z * e[1][2] + e[1][3],
+                   v.x * e[2][0] + v.y * e[2][1] + v.z * e[2][2] + e[2][3]);
+}
+
+// ---- src/camera.rs:45-64 ------------------------------------------------------------
+Camera::Camera(Vector3 eye_, Vector3 target, Vector3 y_up, double v_fov, LensShape shape, double aperture,
+               double focus) {
+    lens_radius = 0.5 * aperture;
+    // f64::to_radians is `self * (PI / 180.0)`; note the FULL fov is used as the half angle
+    double plane_half_height = std::tan(v_fov * (config::PI / 180.0));
+    forward = (target - eye_).normalize();
+    right = forward.cross(y_up).normalize();
+    up = right.cross(forward).normalize();
+    eye = eye_;
+    lens_shape = shape;
+    focus_distance = focus;
+    plane_half_right = right * plane_half_height * focus;
+    plane_half_up = up * plane_half_height * focus;
+}
+hnm_camera Camera::abi() const {
+    hnm_camera c;
+    memset(&c, 0, sizeof(c));
+    c.eye = eye.abi(); c.right = right.abi(); c.up = up.abi(); c.forward = forward.abi();
+    c.plane_half_right = plane_half_right.abi(); c.plane_half_up = plane_half_up.abi();
+    c.lens_radius = lens_radius; c.focus_distance = focus_distance;
+    c.lens_shape = (int32_t)lens_shape;
+    return c;
+}
+
+// ---- src/loader.rs:12-59 ---------------------------------------------------------------
+static std::vector<std::string> split_char(const std::string& s, char sep) {  // str::split(" ")
+    std::vector<std::string> out;
+    size_t start = 0;
+    for (;;) {
+        size_t p = s.find(sep, start);
+        if (p == std::string::npos) { out.push_back(s.substr(start)); break; }
+        out.push_back(s.substr(start, p - start));
+        start = p + 1;
+    }
+    return out;
+}
+static double parse_f64(const std::string& s) {
+    // Rust `parse::<f64>()`: whole string must be a number, correctly rounded (as is strtod)
+    if (s.empty()) throw std::runtime_error("obj: empty float field (the reference would panic here)");
+    char* end = nullptr;
+    double v = std::strtod(s.c_str(), &end);
+    if (end == s.c_str() || *end != '\0') throw std::runtime_error("obj: bad float '" + s + "'");
+    return v;
+}
+static size_t parse_usize(const std::string& s) {
+    if (s.empty()) throw std::runtime_error("obj: empty index field (the reference would panic here)");
+    char* end = nullptr;
+    unsigned long long v = std::strtoull(s.c_str(), &end, 10);
+    if (end == s.c_str() || *end != '\0' || s[0] == '-' || s[0] == ' ') throw std::runtime_error("obj: bad index '" + s + "'");
+    return (size_t)v;
+}
+ObjGeometry parse_obj(const std::string& text) {
+    ObjGeometry g;
+    size_t pos = 0;
+    while (pos < text.size()) {
+        size_t nl = text.find('\n', pos);
+        std::string l = text.substr(pos, nl == std::string::npos ? std::string::npos : nl - pos);
+        pos = (nl == std::string::npos) ? text.size() : nl + 1;
+        if (!l.empty() && l.back() == '\r') l.pop_back();  // BufRead::lines strips "\r\n"
+        std::vector<std::string> sp = split_char(l, ' ');
+        if (sp[0] == "v") {
+            if (sp.size() < 4) throw std::runtime_error("obj: short v line");
+            g.vertexes.push_back(Vector3(parse_f64(sp[1]), parse_f64(sp[2]), parse_f64(sp[3])));
+        } else if (sp[0] == "f") {
+            if (sp.size() < 4) throw std::runtime_error("obj: short f line");
+            size_t a = parse_usize(split_char(sp[1], '/')[0]) - 1;
+            size_t b = parse_usize(split_char(sp[2], '/')[0]) - 1;
+            size_t c = parse_usize(split_char(sp[3], '/')[0]) - 1;
+            g.faces.push_back((uint32_t)a); g.faces.push_back((uint32_t)b); g.faces.push_back((uint32_t)c);
+            if (sp.size() == 5) {  // quad -> (a, c, d)
+                size_t d = parse_usize(split_char(sp[4], '/')[0]) - 1;
+                g.faces.push_back((uint32_t)a); g.faces.push_back((uint32_t)c); g.faces.push_back((uint32_t)d);
+            }
+        }
+    }
+    return g;
+}
+
+Mesh ObjLoader::load(const AssetStore& assets, const std::string& path, const Matrix44& matrix, Material material) {
+    std::shared_ptr<ObjGeometry> g = assets.obj(path);
+    Mesh mesh;
+    mesh.material = std::move(material);
+    mesh.vertexes.reserve(g->vertexes.size());
+    for (const Vector3& v : g->vertexes) mesh.vertexes.push_back(matrix * v);
+    for (size_t i = 0; i + 2 < g->faces.size(); i += 3) mesh.faces.push_back(Face{g->faces[i], g->faces[i + 1], g->faces[i + 2]});
+    return mesh;
+}
+
+// ---- asset store ----------------------------------------------------------------------------
+static bool read_all(const std::string& path, std::string& out) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    std::ostringstream ss;
+    ss << f.rdbuf();
+    out = ss.str();
+    return true;
+}
+
+std::shared_ptr<ObjGeometry> AssetStore::obj(const std::string& path) const {
+    auto it = objs_.find(path);
+    if (it != objs_.end()) return it->second;
+    if (!root_.empty()) {
+        std::string text;
+        if (read_all(root_ + "/" + path, text)) {
+            auto g = std::make_shared<ObjGeometry>(parse_obj(text));
+            objs_[path] = g;
+            return g;
+        }
+    }
+    throw std::runtime_error("asset not found: " + path);
+}
+std::shared_ptr<Image> AssetStore::image(const std::string& path) const {
+    auto it = images_.find(path);
+    if (it != images_.end()) return it->second;
+    throw std::runtime_error("image asset not found (decode it on the host and register it, or load a pack): " + path);
+}
+
+// pack layout (little endian), written by tools/make_asset_pack.py:
+//   "HNMPACK1" u32 count { u32 name_len, name, u32 kind(1 mesh | 2 image), u32 a, u32 b, u64 raw, u64 comp, zlib bytes }
+//   mesh : a = vertex count, b = face count; payload = f64 xyz[a] then u32 v0v1v2[b]
+//   image: a = width, b = height;           payload = RGBA8 rows, top row first
+bool AssetStore::load_pack(const std::string& path, std::string* err) {
+    std::string buf;
+    if (!read_all(path, buf)) { if (err) *err = "cannot read " + path; return false; }
+    const uint8_t* p = (const uint8_t*)buf.data();
+    const uint8_t* end = p + buf.size();
+    auto need = [&](size_t n) { if ((size_t)(end - p) < n) throw std::runtime_error("truncated pack"); };
+    auto rd32 = [&]() { need(4); uint32_t v; memcpy(&v, p, 4); p += 4; return v; };
+    auto rd64 = [&]() { need(8); uint64_t v; memcpy(&v, p, 8); p += 8; return v; };
+    try {
+        need(8);
+        if (memcmp(p, "HNMPACK1", 8) != 0) throw std::runtime_error("bad pack magic");
+        p += 8;
+        uint32_t count = rd32();
+        for (uint32_t i = 0; i < count; i++) {
+            uint32_t nl = rd32();
+            need(nl);
+            std::string name((const char*)p, nl);
+            p += nl;
+            uint32_t kind = rd32(), a = rd32(), b = rd32();
+            uint64_t raw = rd64(), comp = rd64();
+            need(comp);
+            std::vector<uint8_t> data(raw);
+            uLongf dl = (uLongf)raw;
+            if (uncompress(data.data(), &dl, p, (uLong)comp) != Z_OK || dl != raw) throw std::runtime_error("zlib failure in " + name);
+            p += comp;
+            if (kind == 1) {
+                if (raw != (uint64_t)a * 24 + (uint64_t)b * 12) throw std::runtime_error("bad mesh size " + name);
+                auto g = std::make_shared<ObjGeometry>();
+                g->vertexes.resize(a);
+                for (uint32_t k = 0; k < a; k++) {
+                    double xyz[3];
+                    memcpy(xyz, data.data() + (size_t)k * 24, 24);
+                    g->vertexes[k] = Vector3(xyz[0], xyz[1], xyz[2]);
+                }
+                g->faces.resize((size_t)b * 3);
+                memcpy(g->faces.data(), data.data() + (size_t)a * 24, (size_t)b * 12);
+                objs_[name] = g;
+            } else if (kind == 2) {
+                if (raw != (uint64_t)a * b * 4) throw std::runtime_error("bad image size " + name);
+                auto img = std::make_shared<Image>();
+                img->width = a; img->height = b;
+                img->rgba = std::move(data);
+                images_[name] = img;
+            } else {
+                throw std::runtime_error("unknown pack entry kind");
+            }
+        }
+    } catch (const std::exception& e) {
+        if (err) *err = e.what();
+        return false;
+    }
+    return true;
+}
+
+// ---- src/bvh.rs -------------------------------------------------------------------------------
+bool Aabb::intersect_aabb(const Aabb& o) const {
+    return min.x < o.max.x && max.x > o.min.x && min.y < o.max.y && max.y > o.min.y && min.z < o.max.z && max.z > o.min.z;
+}
+void Aabb::merge(const Aabb& o) {  // f64::min / f64::max
+    min.x = std::fmin(min.x, o.min.x); min.y = std::fmin(min.y, o.min.y); min.z = std::fmin(min.z, o.min.z);
+    max.x = std::fmax(max.x, o.max.x); max.y = std::fmax(max.y, o.max.y); max.z = std::fmax(max.z, o.max.z);
+}
+static Aabb aabb_from_triangle(const Vector3& v0, const Vector3& v1, const Vector3& v2) {
+    Aabb a;
+    a.min = Vector3(std::fmin(std::fmin(v0.x, v1.x), v2.x), std::fmin(std::fmin(v0.y, v1.y), v2.y), std::fmin(std::fmin(v0.z, v1.z), v2.z));
+    a.max = Vector3(std::fmax(std::fmax(v0.x, v1.x), v2.x), std::fmax(std::fmax(v0.y, v1.y), v2.y), std::fmax(std::fmax(v0.z, v1.z), v2.z));
+    return a;
+}
+static std::unique_ptr<BvhNode> empty_node() {
+    auto n = std::make_unique<BvhNode>();
+    n->aabb.min = Vector3::from_one(config::INF);
+    n->aabb.max = Vector3::from_one(-config::INF);
+    return n;
+}
+// 0 = x, 1 = y, 2 = z (src/bvh.rs:125,134,143: strict comparisons, ties fall through to z)
+static int split_axis(const Aabb& a) {
+    double lx = a.max.x - a.min.x, ly = a.max.y - a.min.y, lz = a.max.z - a.min.z;
+    if (lx > ly && lx > lz) return 0;
+    if (ly > lx && ly > lz) return 1;
+    return 2;
+}
+static double comp(const Vector3& v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+
+// src/bvh.rs:107-153
+static std::unique_ptr<BvhNode> build_mesh_rec(const Mesh& mesh, std::vector<size_t>& idx) {
+    auto node = empty_node();
+    for (size_t fi : idx) {
+        const Face& f = mesh.faces[fi];
+        node->aabb.merge(aabb_from_triangle(mesh.vertexes[f.v0], mesh.vertexes[f.v1], mesh.vertexes[f.v2]));
+    }
+    size_t mid = idx.size() / 2;
+    if (mid <= 2) {
+        node->indexes = idx;
+    } else {
+        int axis = split_axis(node->aabb);
+        // slice::sort_by is a stable sort; partial_cmp(..).unwrap() would panic on NaN
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+            const Face& fa = mesh.faces[a];
+            const Face& fb = mesh.faces[b];
+            double sa = comp(mesh.vertexes[fa.v0], axis) + comp(mesh.vertexes[fa.v1], axis) + comp(mesh.vertexes[fa.v2], axis);
+            double sb = comp(mesh.vertexes[fb.v0], axis) + comp(mesh.vertexes[fb.v1], axis) + comp(mesh.vertexes[fb.v2], axis);
+            return sa < sb;
+        });
+        std::vector<size_t> second(idx.begin() + mid, idx.end());  // split_off(mid)
+        idx.resize(mid);
+        node->children.push_back(build_mesh_rec(mesh, idx));
+        node->children.push_back(build_mesh_rec(mesh, second));
+    }
+    return node;
+}
+std::unique_ptr<BvhNode> build_from_mesh(const Mesh& mesh) {
+    std::vector<size_t> idx(mesh.faces.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
+    return build_mesh_rec(mesh, idx);
+}
+// src/bvh.rs:155-201
+static std::unique_ptr<BvhNode> build_scene_rec(const Scene& scene, std::vector<size_t>& idx) {
+    auto node = empty_node();
+    for (size_t i : idx) node->aabb.merge(scene.elements[i]->aabb());
+    size_t mid = idx.size() / 2;
+    if (mid <= 2) {
+        node->indexes = idx;
+    } else {
+        int axis = split_axis(node->aabb);
+        std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) {
+            Aabb aa = scene.elements[a]->aabb(), ab = scene.elements[b]->aabb();
+            double sa = comp(aa.min, axis) + comp(aa.max, axis);
+            double sb = comp(ab.min, axis) + comp(ab.max, axis);
+            return sa < sb;
+        });
+        std::vector<size_t> second(idx.begin() + mid, idx.end());
+        idx.resize(mid);
+        node->children.push_back(build_scene_rec(scene, idx));
+        node->children.push_back(build_scene_rec(scene, second));
+    }
+    return node;
+}
+std::unique_ptr<BvhNode> build_from_scene(const Scene& scene) {
+    std::vector<size_t> idx(scene.elements.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = i;
+    return build_scene_rec(scene, idx);
+}
+
+// ---- src/scene.rs ----------------------------------------------------------------------------------
+Aabb Sphere::aabb() const { return Aabb{center - Vector3::from_one(radius), center + Vector3::from_one(radius)}; }
+std::unique_ptr<BvhMesh> BvhMesh::from_mesh(Mesh mesh) {
+    auto m = std::make_unique<BvhMesh>();
+    m->bvh = build_from_mesh(mesh);
+    m->mesh = std::move(mesh);
+    return m;
+}
+bool Scene::add_with_check_collisions(std::unique_ptr<Intersectable> e) {
+    Aabb a = e->aabb();
+    for (const auto& o : elements)
+        if (o->aabb().intersect_aabb(a)) return false;
+    elements.push_back(std::move(e));
+    return true;
+}
+std::vector<uint32_t> Scene::emissions() const {
+    std::vector<uint32_t> out;
+    for (size_t i = 0; i < elements.size(); i++)
+        if (elements[i]->nee_available() && elements[i]->material().emission.color != Color::zero()) out.push_back((uint32_t)i);
+    return out;
+}
+
+// ---- flattening ---------------------------------------------------------------------------------------
+int32_t FlatSceneBuilder::add_image(const std::shared_ptr<Image>& img) {
+    if (!img) return -1;
+    auto it = image_ids_.find(img.get());
+    if (it != image_ids_.end()) return it->second;
+    int32_t id = (int32_t)out_.images.size();
+    out_.images.push_back(hnm_image{img->rgba.data(), img->width, img->height});
+    out_.image_refs.push_back(img);
+    image_ids_[img.get()] = id;
+    return id;
+}
+int32_t FlatSceneBuilder::add_material(const Material& m) {
+    hnm_material hm;
+    memset(&hm, 0, sizeof(hm));
+    auto tex = [&](const Texture& t) {
+        hnm_texture ht;
+        memset(&ht, 0, sizeof(ht));
+        ht.color = t.color.abi();
+        ht.image = add_image(t.image_texture);
+        return ht;
+    };
+    hm.albedo = tex(m.albedo); hm.emission = tex(m.emission); hm.roughness = tex(m.roughness);
+    hm.param = m.surface.param; hm.surface = m.surface.tag;
+    out_.materials.push_back(hm);
+    return (int32_t)out_.materials.size() - 1;
+}
+void FlatSceneBuilder::flatten_tree(const BvhNode& root, std::vector<hnm_bvh_node>& nodes, std::vector<uint32_t>& indices,
+                                    uint32_t index_base) {
+    // DFS pre-order == the reference's recursion order (src/bvh.rs:213-263)
+    struct Rec {
+        static uint32_t go(const BvhNode& n, std::vector<hnm_bvh_node>& nodes, std::vector<uint32_t>& indices, uint32_t index_base) {
+            uint32_t me = (uint32_t)nodes.size();
+            nodes.push_back(hnm_bvh_node{});
+            hnm_bvh_node h;
+            memset(&h, 0, sizeof(h));
+            h.aabb_min[0] = n.aabb.min.x; h.aabb_min[1] = n.aabb.min.y; h.aabb_min[2] = n.aabb.min.z;
+            h.aabb_max[0] = n.aabb.max.x; h.aabb_max[1] = n.aabb.max.y; h.aabb_max[2] = n.aabb.max.z;
+            if (n.children.empty()) {
+                h.child0 = h.child1 = -1;
+                h.first = (uint32_t)indices.size() - index_base;
+                h.count = (uint32_t)n.indexes.size();
+                for (size_t i : n.indexes) indices.push_back((uint32_t)i);
+            } else {
+                h.child0 = (int32_t)go(*n.children[0], nodes, indices, index_base);
+                h.child1 = (int32_t)go(*n.children[1], nodes, indices, index_base);
+            }
+            nodes[me] = h;
+            return me;
+        }
+    };
+    Rec::go(root, nodes, indices, index_base);
+}
+void FlatSceneBuilder::add_sphere(const Sphere& s) {
+    hnm_element e;
+    memset(&e, 0, sizeof(e));
+    e.kind = HNM_ELEM_SPHERE; e.a = s.center.abi(); e.radius = s.radius; e.mesh = -1;
+    e.material = add_material(s.mat);
+    out_.elements.push_back(e);
+}
+void FlatSceneBuilder::add_cuboid(const Cuboid& c) {
+    hnm_element e;
+    memset(&e, 0, sizeof(e));
+    e.kind = HNM_ELEM_CUBOID; e.a = c.box.min.abi(); e.b = c.box.max.abi(); e.mesh = -1;
+    e.material = add_material(c.mat);
+    out_.elements.push_back(e);
+}
+void FlatSceneBuilder::add_mesh(const BvhMesh& m) {
+    hnm_mesh hm;
+    memset(&hm, 0, sizeof(hm));
+    hm.vertex_offset = (uint32_t)(out_.vertices.size() / 3);
+    hm.vertex_count = (uint32_t)m.mesh.vertexes.size();
+    for (const Vector3& v : m.mesh.vertexes) { out_.vertices.push_back(v.x); out_.vertices.push_back(v.y); out_.vertices.push_back(v.z); }
+    hm.face_offset = (uint32_t)(out_.faces.size() / 3);
+    hm.face_count = (uint32_t)m.mesh.faces.size();
+    for (const Face& f : m.mesh.faces) { out_.faces.push_back((uint32_t)f.v0); out_.faces.push_back((uint32_t)f.v1); out_.faces.push_back((uint32_t)f.v2); }
+    hm.node_offset = (uint32_t)out_.mesh_nodes.size();
+    hm.index_offset = (uint32_t)out_.mesh_indices.size();
+    std::vector<hnm_bvh_node> nodes;
+    flatten_tree(*m.bvh, nodes, out_.mesh_indices, hm.index_offset);
+    // child links are relative to this mesh's node_offset
+    out_.mesh_nodes.insert(out_.mesh_nodes.end(), nodes.begin(), nodes.end());
+    hm.node_count = (uint32_t)nodes.size();
+    hm.index_count = (uint32_t)out_.mesh_indices.size() - hm.index_offset;
+    hnm_element e;
+    memset(&e, 0, sizeof(e));
+    e.kind = HNM_ELEM_MESH; e.mesh = (int32_t)out_.meshes.size();
+    e.a = m.bvh->aabb.min.abi(); e.b = m.bvh->aabb.max.abi();
+    e.material = add_material(m.mesh.material);
+    out_.meshes.push_back(hm);
+    out_.elements.push_back(e);
+}
+void Sphere::flatten(FlatSceneBuilder& b) const { b.add_sphere(*this); }
+void Cuboid::flatten(FlatSceneBuilder& b) const { b.add_cuboid(*this); }
+void BvhMesh::flatten(FlatSceneBuilder& b) const { b.add_mesh(*this); }
+
+void FlatScene::finalize() {
+    memset(&desc, 0, sizeof(desc));
+    desc.abi_version = HNM_ABI_VERSION;
+    desc.elements = elements.data(); desc.num_elements = (uint32_t)elements.size();
+    desc.materials = materials.data(); desc.num_materials = (uint32_t)materials.size();
+    desc.images = images.data(); desc.num_images = (uint32_t)images.size();
+    desc.meshes = meshes.data(); desc.num_meshes = (uint32_t)meshes.size();
+    desc.vertices = vertices.data(); desc.num_vertices = (uint32_t)(vertices.size() / 3);
+    desc.faces = faces.data(); desc.num_faces = (uint32_t)(faces.size() / 3);
+    desc.mesh_nodes = mesh_nodes.data(); desc.num_mesh_nodes = (uint32_t)mesh_nodes.size();
+    desc.mesh_indices = mesh_indices.data(); desc.num_mesh_indices = (uint32_t)mesh_indices.size();
+    desc.top_nodes = top_nodes.data(); desc.num_top_nodes = (uint32_t)top_nodes.size();
+    desc.top_indices = top_indices.data(); desc.num_top_indices = (uint32_t)top_indices.size();
+    desc.emissions = emissions.data(); desc.num_emissions = (uint32_t)emissions.size();
+    desc.config = config::to_abi();
+}
+
+std::unique_ptr<BvhScene> BvhScene::from_scene(Scene scene) {
+    auto bs = std::make_unique<BvhScene>();
+    bs->bvh = build_from_scene(scene);
+    bs->scene = std::move(scene);
+    FlatSceneBuilder b(bs->flat);
+    for (const auto& e : bs->scene.elements) e->flatten(b);
+    FlatSceneBuilder::flatten_tree(*bs->bvh, bs->flat.top_nodes, bs->flat.top_indices, 0);
+    bs->flat.emissions = bs->scene.emissions();
+    const Skybox& sb = bs->scene.skybox;
+    bs->flat.finalize();
+    const std::shared_ptr<Image> faces[6] = {sb.px, sb.nx, sb.py, sb.ny, sb.pz, sb.nz};
+    for (int i = 0; i < 6; i++) bs->flat.desc.skybox_images[i] = b.add_image(faces[i]);
+    bs->flat.desc.skybox_intensity = sb.intensity.abi();
+    // add_image may have grown the image table
+    bs->flat.desc.images = bs->flat.images.data();
+    bs->flat.desc.num_images = (uint32_t)bs->flat.images.size();
+    return bs;
+}
+
+// ---- scene authoring (src/main.rs) ---------------------------------------------------------------------
+static Skybox make_skybox(const AssetStore& a, const std::string& dir, Vector3 intensity) {
+    Skybox s;
+    s.px = a.image(dir + "/posx.jpg"); s.nx = a.image(dir + "/negx.jpg");
+    s.py = a.image(dir + "/posy.jpg"); s.ny = a.image(dir + "/negy.jpg");
+    s.pz = a.image(dir + "/posz.jpg"); s.nz = a.image(dir + "/negz.jpg");
+    s.intensity = intensity;
+    return s;
+}
+static Texture tex_path(const AssetStore& a, const std::string& p) { return Texture::from_image(a.image(p)); }
+static double fract(double v) { return v - std::trunc(v); }
+
+// camera + light + mirror + frame + floor of the submitted scene; shared by the
+// default scene and the two builder-defined benchmark scenes
+static SceneAndCamera rtcamp6_stage(const AssetStore& a, double aperture, double focus, bool with_bunny_and_mirror) {
+    const double scene_scale = 1.0;
+    double theta = config::PI2 * 0.03;
+    double r = 6.5 * scene_scale;
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(r * std::sin(theta), 2.0 * scene_scale, r * std::cos(theta)), Vector3(0.0, 1.0 * scene_scale, 0.0),
+                       Vector3(0.0, 1.0, 0.0).normalize(), 20.0, LensShape::Circle, aperture, focus * scene_scale);
+    double radius = 0.2;
+    double floor_s = 9.0 * scene_scale;
+    Scene& scene = sc.scene;
+    scene.add(std::make_unique<Sphere>(Vector3(-0.3, 0.5 + radius, 0.0) * scene_scale, radius * scene_scale,
+                                       Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color(30.0, 20.0, 4.0)), Texture::black()}));
+    if (with_bunny_and_mirror) {
+        scene.add(BvhMesh::from_mesh(ObjLoader::load(
+            a, "models/bunny/bunny_wired_300.obj",
+            Matrix44::scale_linear(1.5 * scene_scale) * Matrix44::translate(0.0, 0.0, 0.0) * Matrix44::rotate_y(0.3),
+            Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 0.01, 0.01)), Texture::black(), Texture::from_color(Color::from_one(0.05))})));
+        scene.add(BvhMesh::from_mesh(ObjLoader::load(
+            a, "models/box.obj",
+            Matrix44::translate(1.0 * scene_scale, 0.0, -3.0 * scene_scale) * Matrix44::rotate_y(-config::PI / 8.0) *
+                Matrix44::scale(4.0 * 0.9 * scene_scale, 3.0 * 0.9 * scene_scale, 0.1 * 0.9 * scene_scale),
+            Material{SurfaceType::Specular(), Texture::white(), Texture::black(), Texture::black()})));
+        scene.add(BvhMesh::from_mesh(ObjLoader::load(
+            a, "models/picture_frame.obj",
+            Matrix44::translate(1.0 * scene_scale, 0.0, -3.0 * scene_scale) * Matrix44::rotate_y(-config::PI / 8.0) *
+                Matrix44::scale(4.0 * scene_scale, 3.0 * scene_scale, scene_scale),
+            Material{SurfaceType::GGX(0.9), Texture::from_color(Color(0.33, 0.27, 0.22)), Texture::black(), Texture::from_color(Color::from_one(0.3))})));
+    }
+    scene.add(std::make_unique<Cuboid>(Aabb{Vector3(-floor_s, -1.0, -floor_s), Vector3(floor_s, 0.0, floor_s)},
+                                       Material{SurfaceType::Diffuse(), tex_path(a, "textures/2d/magic-circle3.png"), Texture::black(), Texture::white()}));
+    scene.skybox = make_skybox(a, "textures/cube/Powerlines", Vector3::from_one(1.0));
+    return sc;
+}
+
+// src/main.rs:1020-1153
+SceneAndCamera init_scene_rtcamp6_v3_1(const AssetStore& a) {
+    const double scene_scale = 1.0;
+    SceneAndCamera sc = rtcamp6_stage(a, 0.03, 5.0, true);
+    int count = 6;
+    for (int i = 0; i < count; i++) {
+        double r = 2.2 * scene_scale;
+        double dr = (double)i / (double)count;
+        double theta = config::PI2 * dr;
+        double px = r * std::sin(theta), py = 0.0, pz = r * std::cos(theta);
+        double s = scene_scale;
+        double offset = 0.45;
+        Material m = (i % 2 == 0)
+                         ? Material{SurfaceType::Refraction(1.5), Texture::from_color(hsv_to_rgb(Color(fract(offset + dr), 0.2, 1.0))),
+                                    Texture::black(), Texture::from_color(Color::from_one(0.1))}
+                         : Material{SurfaceType::GGX(0.8), Texture::from_color(hsv_to_rgb(Color(fract(offset + dr), 1.0, 1.0))),
+                                    Texture::black(), Texture::from_color(Color::from_one(0.05 * (double)i))};
+        sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+            a, "models/armadilo_1000.obj", Matrix44::translate(px, py, pz) * Matrix44::rotate_y(theta) * Matrix44::scale_linear(s), std::move(m))));
+    }
+    return sc;
+}
+
+// src/main.rs:1155-1212
+SceneAndCamera init_scene_rtcamp6_v4(const AssetStore& a) {
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 1.0, 6.0), Vector3(0.0, 0.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 30.0, LensShape::Circle,
+                       0.2 * 0.0, 4.9);
+    sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/fractal_icosahedron.obj", Matrix44::scale_linear(1.0) * Matrix44::translate(0.0, 0.0, 0.0) * Matrix44::rotate_y(0.3),
+        Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 1.0, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.05))})));
+    sc.scene.add(std::make_unique<Sphere>(sc.camera.eye - sc.camera.forward, 0.001,
+                                          Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color::from_one(1000.0)), Texture::black()}));
+    sc.scene.skybox = make_skybox(a, "textures/cube/Ryfjallet", Vector3::from_one(1.0));
+    return sc;
+}
+
+// src/main.rs:54-131 (init_scene_simple) and :133-250 (init_scene_material_examples)
+static SceneAndCamera simple_stage(const AssetStore& a, double aperture, SurfaceType floor_surface) {
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 2.0, 9.0), Vector3(0.0, 1.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 10.0, LensShape::Circle, aperture, 8.8);
+    sc.scene.add(std::make_unique<Cuboid>(
+        Aabb{Vector3(-5.0, -1.0, -5.0), Vector3(5.0, 0.0, 5.0)},
+        Material{floor_surface, tex_path(a, "textures/2d/checkered_diagonal_10_0.5_1.0_512.png"), Texture::black(),
+                 tex_path(a, "textures/2d/checkered_diagonal_10_0.1_0.6_512.png")}));
+    return sc;
+}
+static SceneAndCamera scene_simple(const AssetStore& a, const std::string& sky) {
+    double radius = 0.6;
+    SceneAndCamera st = simple_stage(a, 0.2 * 0.0, SurfaceType::GGX(0.8));
+    SceneAndCamera sc;
+    sc.camera = st.camera;
+    sc.scene.add(std::make_unique<Sphere>(Vector3(0.0, radius, 0.0), radius,
+                                          Material{SurfaceType::Diffuse(), Texture::white(), Texture::black(), Texture::from_color(Color::from_one(0.99))}));
+    sc.scene.add(std::make_unique<Sphere>(Vector3(3.0, 2.0 + radius, -2.0), radius * 0.2,
+                                          Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color(200.0, 10.0, 10.0)), Texture::from_color(Color::from_one(0.05))}));
+    sc.scene.add(std::make_unique<Sphere>(Vector3(-3.0, 2.0 + radius, -2.0), radius * 0.2,
+                                          Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color(10.0, 200.0, 10.0)), Texture::from_color(Color::from_one(0.05))}));
+    sc.scene.add(std::move(st.scene.elements[0]));
+    sc.scene.skybox = make_skybox(a, sky, Vector3::zero());
+    return sc;
+}
+SceneAndCamera init_scene_simple(const AssetStore& a) { return scene_simple(a, "textures/cube/LancellottiChapel"); }
+static SceneAndCamera scene_material_examples(const AssetStore& a, const std::string& sky) {
+    double radius = 0.4;
+    SceneAndCamera st = simple_stage(a, 0.2, SurfaceType::Diffuse());
+    SceneAndCamera sc;
+    sc.camera = st.camera;
+    Texture rough = Texture::from_color(Color::from_one(0.05));
+    const SurfaceType kinds[5] = {SurfaceType::Diffuse(), SurfaceType::GGX(0.8), SurfaceType::Specular(), SurfaceType::Refraction(1.5),
+                                  SurfaceType::GGXRefraction(1.5)};
+    for (int i = 0; i < 5; i++)
+        sc.scene.add(std::make_unique<Sphere>(Vector3(-2.0 + (double)i, radius, 0.0), radius, Material{kinds[i], Texture::white(), Texture::black(), rough}));
+    sc.scene.add(std::make_unique<Sphere>(Vector3(0.0, 2.0 + radius, -2.0), radius,
+                                          Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color::from_one(20.0)), rough}));
+    sc.scene.add(std::move(st.scene.elements[0]));
+    sc.scene.skybox = make_skybox(a, sky, Vector3::one());
+    return sc;
+}
+SceneAndCamera init_scene_material_examples(const AssetStore& a) { return scene_material_examples(a, "textures/cube/LancellottiChapel"); }
+
+// BASELINE.md config 3 (builder-defined, not a scene of the reference): the
+// default scene plus the two fractal meshes with the materials the reference
+// gives them (src/main.rs:1171-1186 and :907-922), floating above the ring of
+// armadillos.  ~75 k triangles / ~44 k BVH nodes.
+SceneAndCamera init_scene_bvh_heavy(const AssetStore& a) {
+    SceneAndCamera sc = init_scene_rtcamp6_v3_1(a);
+    sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/fractal_icosahedron.obj", Matrix44::translate(-2.2, 2.7, -1.2) * Matrix44::rotate_y(0.3) * Matrix44::scale_linear(0.4),
+        Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 1.0, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.05))})));
+    sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/fractal_dodecahedron.obj", Matrix44::translate(2.3, 2.5, -0.6) * Matrix44::rotate_y(0.0) * Matrix44::scale_linear(0.4),
+        Material{SurfaceType::Refraction(1.5), Texture::from_color(Color(0.7, 0.7, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.1))})));
+    return sc;
+}
+
+// BASELINE.md config 4 (builder-defined): round_brilliant.obj instances with
+// GGXRefraction{2.42} on the textured floor, strong DoF (the commented
+// alternative at src/main.rs:1035-1036: aperture 0.3, focus 5.7).
+SceneAndCamera init_scene_diamond(const AssetStore& a) {
+    SceneAndCamera sc = rtcamp6_stage(a, 0.3, 5.7, false);
+    sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/round_brilliant.obj", Matrix44::translate(0.0, 0.01, 0.0) * Matrix44::rotate_y(0.3) * Matrix44::scale_linear(0.8),
+        Material{SurfaceType::GGXRefraction(2.42), Texture::from_color(Color(1.0, 1.0, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.02))})));
+    int count = 6;
+    for (int i = 0; i < count; i++) {
+        double r = 2.2;
+        double dr = (double)i / (double)count;
+        double theta = config::PI2 * dr;
+        sc.scene.add(BvhMesh::from_mesh(ObjLoader::load(
+            a, "models/round_brilliant.obj",
+            Matrix44::translate(r * std::sin(theta), 0.01, r * std::cos(theta)) * Matrix44::rotate_y(theta) * Matrix44::scale_linear(0.45),
+            Material{SurfaceType::GGXRefraction(2.42), Texture::from_color(hsv_to_rgb(Color(fract(0.45 + dr), 0.2, 1.0))), Texture::black(),
+                     Texture::from_color(Color::from_one(0.02 + 0.02 * (double)i))})));
+    }
+    return sc;
+}
+
+SceneAndCamera init_scene_by_name(const std::string& name, const AssetStore& a) {
+    if (name == "rtcamp6" || name == "rtcamp6_v3_1") return init_scene_rtcamp6_v3_1(a);
+    if (name == "rtcamp6_v4") return init_scene_rtcamp6_v4(a);
+    if (name == "simple") return init_scene_simple(a);
+    if (name == "material_examples") return init_scene_material_examples(a);
+    // the same two scenes under the (much smaller) Powerlines cubemap, so that they fit the committed asset pack
+    if (name == "simple_pl") return scene_simple(a, "textures/cube/Powerlines");
+    if (name == "material_examples_pl") return scene_material_examples(a, "textures/cube/Powerlines");
+    if (name == "bvh_heavy") return init_scene_bvh_heavy(a);
+    if (name == "diamond") return init_scene_diamond(a);
+    throw std::runtime_error("unknown scene: " + name);
+}
+
+std::vector<std::string> scene_asset_paths(const std::string& name, bool images) {
+    auto cube = [](const std::string& d) {
+        return std::vector<std::string>{d + "/posx.jpg", d + "/negx.jpg", d + "/posy.jpg", d + "/negy.jpg", d + "/posz.jpg", d + "/negz.jpg"};
+    };
+    std::vector<std::string> out;
+    auto add = [&](const std::vector<std::string>& v) { out.insert(out.end(), v.begin(), v.end()); };
+    bool rt = (name == "rtcamp6" || name == "rtcamp6_v3_1" || name == "bvh_heavy");
+    if (images) {
+        if (rt || name == "diamond") { add(cube("textures/cube/Powerlines")); out.push_back("textures/2d/magic-circle3.png"); }
+        if (name == "rtcamp6_v4") add(cube("textures/cube/Ryfjallet"));
+        if (name == "simple" || name == "material_examples" || name == "simple_pl" || name == "material_examples_pl") {
+            add(cube(name.size() > 3 && name.substr(name.size() - 3) == "_pl" ? "textures/cube/Powerlines" : "textures/cube/LancellottiChapel"));
+            out.push_back("textures/2d/checkered_diagonal_10_0.5_1.0_512.png");
+            out.push_back("textures/2d/checkered_diagonal_10_0.1_0.6_512.png");
+        }
+    } else {
+        if (rt) add({"models/bunny/bunny_wired_300.obj", "models/box.obj", "models/picture_frame.obj", "models/armadilo_1000.obj"});
+        if (name == "bvh_heavy") add({"models/fractal_icosahedron.obj", "models/fractal_dodecahedron.obj"});
+        if (name == "rtcamp6_v4") out.push_back("models/fractal_icosahedron.obj");
+        if (name == "diamond") out.push_back("models/round_brilliant.obj");
+    }
+    return out;
+}
+
+}  // namespace hanamaru
