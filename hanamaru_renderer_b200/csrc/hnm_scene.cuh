@@ -1,0 +1,406 @@
+// hnm_scene.cuh -- hnm_scene: validation of the host description, GPU re-layout of the two BVH
+// levels into ONE tree of 64-byte two-child nodes with conservative f32 boxes, triangles gathered
+// in the reference's leaf order with precomputed edges, textures as CUDA texture objects.
+#ifndef HNM_SCENE_CUH
+#define HNM_SCENE_CUH
+
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hnm_device.cuh"
+
+namespace hnm {
+
+extern thread_local std::string g_last_error;
+inline int set_error(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+#define HNM_CUDA(call)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return hnm::set_error(HNM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+}  // namespace hnm
+
+struct hnm_scene {
+    int device = 0;
+    hnm::DScene d;
+    hnm_config config;
+    std::vector<void*> allocs;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> texs;
+    uint32_t num_nodes = 0, num_tris = 0, num_elements = 0, num_emissions = 0;
+    std::vector<int32_t> elem_surface;  // host copy, per element
+};
+
+namespace hnm {
+
+struct BoxD {
+    double lo[3], hi[3];
+    bool empty = true;
+    void grow(const BoxD& o) {
+        if (o.empty) return;
+        if (empty) { *this = o; return; }
+        for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], o.lo[k]); hi[k] = std::fmax(hi[k], o.hi[k]); }
+    }
+};
+inline BoxD box_of(const double* mn, const double* mx) {
+    BoxD b;
+    b.empty = !(mn[0] <= mx[0] && mn[1] <= mx[1] && mn[2] <= mx[2]);  // the builder's INF/-INF box of an empty node
+    for (int k = 0; k < 3; k++) { b.lo[k] = mn[k]; b.hi[k] = mx[k]; }
+    return b;
+}
+inline float f32_down(double v) {
+    float f = (float)v;
+    if ((double)f > v) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+inline float f32_up(double v) {
+    float f = (float)v;
+    if ((double)f < v) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
+class SceneBuilder {
+  public:
+    SceneBuilder(const hnm_scene_desc* d) : d_(d) {}
+    std::vector<DNode> nodes;
+    std::vector<DTri> tris;
+    std::vector<uint32_t> tri_elem, tri_face;
+    std::vector<uint32_t> elem_seq;
+    BoxD bounds;
+    double pad = 0.0;
+    std::string error;
+
+    bool validate() {
+        const hnm_scene_desc* d = d_;
+        auto fail = [&](const char* m) { error = m; return false; };
+        if (!d) return fail("null scene description");
+        if (d->abi_version != HNM_ABI_VERSION) return fail("abi_version mismatch");
+        if (d->num_elements == 0 || !d->elements) return fail("scene has no elements");
+        if (d->num_top_nodes == 0 || !d->top_nodes) return fail("scene has no top-level BVH");
+        if (d->config.supersampling == 0 || d->config.supersampling > 8) return fail("supersampling out of range");
+        if (d->config.bounce_limit < 2 || d->config.bounce_limit > 64) return fail("bounce_limit out of range");
+        for (uint32_t i = 0; i < d->num_elements; i++) {
+            const hnm_element& e = d->elements[i];
+            if (e.kind < 0 || e.kind > 2) return fail("bad element kind");
+            if (e.material < 0 || (uint32_t)e.material >= d->num_materials) return fail("bad material index");
+            if (e.kind == HNM_ELEM_MESH && (e.mesh < 0 || (uint32_t)e.mesh >= d->num_meshes)) return fail("bad mesh index");
+        }
+        for (uint32_t i = 0; i < d->num_materials; i++) {
+            const hnm_material& m = d->materials[i];
+            if (m.surface < 0 || m.surface > 4) return fail("bad surface type");
+            const hnm_texture* ts[3] = {&m.albedo, &m.emission, &m.roughness};
+            for (auto t : ts)
+                if (t->image >= (int32_t)d->num_images) return fail("bad image index");
+        }
+        for (uint32_t i = 0; i < d->num_images; i++)
+            if (!d->images[i].rgba || d->images[i].width == 0 || d->images[i].height == 0) return fail("bad image");
+        for (int k = 0; k < 6; k++)
+            if (d->skybox_images[k] < 0 || (uint32_t)d->skybox_images[k] >= d->num_images) return fail("bad skybox image index");
+        for (uint32_t i = 0; i < d->num_meshes; i++) {
+            const hnm_mesh& m = d->meshes[i];
+            if ((uint64_t)m.vertex_offset + m.vertex_count > d->num_vertices) return fail("mesh vertices out of range");
+            if ((uint64_t)m.face_offset + m.face_count > d->num_faces) return fail("mesh faces out of range");
+            if ((uint64_t)m.node_offset + m.node_count > d->num_mesh_nodes || m.node_count == 0) return fail("mesh nodes out of range");
+            if ((uint64_t)m.index_offset + m.index_count > d->num_mesh_indices) return fail("mesh indices out of range");
+            for (uint32_t f = 0; f < m.face_count * 3; f++)
+                if (d->faces[(size_t)m.face_offset * 3 + f] >= m.vertex_count) return fail("face vertex index out of range");
+            for (uint32_t n = 0; n < m.node_count; n++) {
+                const hnm_bvh_node& nd = d->mesh_nodes[m.node_offset + n];
+                if (nd.child0 < 0) {
+                    if ((uint64_t)nd.first + nd.count > m.index_count) return fail("mesh leaf range out of range");
+                } else if ((uint32_t)nd.child0 >= m.node_count || nd.child1 < 0 || (uint32_t)nd.child1 >= m.node_count ||
+                           (uint32_t)nd.child0 <= n || (uint32_t)nd.child1 <= n) {
+                    return fail("mesh node links must point forward (DFS pre-order)");
+                }
+            }
+            for (uint32_t k = 0; k < m.index_count; k++)
+                if (d->mesh_indices[m.index_offset + k] >= m.face_count) return fail("mesh index entry out of range");
+        }
+        for (uint32_t n = 0; n < d->num_top_nodes; n++) {
+            const hnm_bvh_node& nd = d->top_nodes[n];
+            if (nd.child0 < 0) {
+                if ((uint64_t)nd.first + nd.count > d->num_top_indices) return fail("top leaf range out of range");
+            } else if ((uint32_t)nd.child0 >= d->num_top_nodes || nd.child1 < 0 || (uint32_t)nd.child1 >= d->num_top_nodes ||
+                       (uint32_t)nd.child0 <= n || (uint32_t)nd.child1 <= n) {
+                return fail("top node links must point forward (DFS pre-order)");
+            }
+        }
+        for (uint32_t k = 0; k < d->num_top_indices; k++)
+            if (d->top_indices[k] >= d->num_elements) return fail("top index entry out of range");
+        for (uint32_t k = 0; k < d->num_emissions; k++)
+            if (d->emissions[k] >= d->num_elements || d->elements[d->emissions[k]].kind != HNM_ELEM_SPHERE)
+                return fail("emissions must be spheres (only Sphere::sample_on_surface exists, src/scene.rs:92)");
+        return true;
+    }
+
+    bool build() {
+        const hnm_scene_desc* d = d_;
+        // 1. the reference's DFS order of elements, and triangles gathered in (element, leaf) order
+        elem_seq.assign(d->num_elements, 0xFFFFFFFFu);
+        std::vector<uint32_t> order;
+        collect_top(0, order);
+        for (uint32_t s = 0; s < order.size(); s++) {
+            if (elem_seq[order[s]] != 0xFFFFFFFFu) { error = "element listed twice in the top-level BVH"; return false; }
+            elem_seq[order[s]] = s;
+        }
+        mesh_tri_base_.assign(d->num_meshes, 0);
+        std::vector<char> mesh_used(d->num_meshes, 0);
+        for (uint32_t el : order) {
+            const hnm_element& e = d->elements[el];
+            BoxD eb = element_box(e);
+            bounds.grow(eb);
+            if (e.kind != HNM_ELEM_MESH) continue;
+            if (mesh_used[e.mesh]) { error = "mesh shared by two elements"; return false; }
+            mesh_used[e.mesh] = 1;
+            const hnm_mesh& m = d->meshes[e.mesh];
+            mesh_tri_base_[e.mesh] = (uint32_t)tris.size();
+            const double* vb = d->vertices + 3 * (size_t)m.vertex_offset;
+            for (uint32_t k = 0; k < m.index_count; k++) {
+                uint32_t face = d->mesh_indices[m.index_offset + k];
+                const uint32_t* f = d->faces + 3 * (size_t)(m.face_offset + face);
+                DTri t;
+                t.v0x = vb[3 * f[0]]; t.v0y = vb[3 * f[0] + 1]; t.v0z = vb[3 * f[0] + 2];
+                // edge1 = v1 - v0, edge2 = v2 - v0 (src/bvh.rs:268-269)
+                t.e1x = vb[3 * f[1]] - t.v0x; t.e1y = vb[3 * f[1] + 1] - t.v0y; t.e1z = vb[3 * f[1] + 2] - t.v0z;
+                t.e2x = vb[3 * f[2]] - t.v0x; t.e2y = vb[3 * f[2] + 1] - t.v0y; t.e2z = vb[3 * f[2] + 2] - t.v0z;
+                tris.push_back(t);
+                tri_elem.push_back(el);
+                tri_face.push_back(face);
+            }
+        }
+        if (tris.size() >= (1u << 26)) { error = "too many triangles for the 26-bit leaf encoding"; return false; }
+        if (d->num_elements >= (1u << 26)) { error = "too many elements"; return false; }
+        double R = 0.0;
+        if (!bounds.empty)
+            for (int k = 0; k < 3; k++) R = std::fmax(R, std::fmax(std::fabs(bounds.lo[k]), std::fabs(bounds.hi[k])));
+        pad = std::fmax(R, 1e-30) * 0x1p-19;  // absolute slack for the f32 rounding of (box - origin)
+        // 2. one tree: node 0 is reserved for the root
+        nodes.clear();
+        nodes.push_back(DNode{});
+        BoxD rb;
+        int32_t root = build_top(0, rb);
+        if (root >= 0) {
+            nodes[0] = nodes[root];
+        } else {
+            DNode n;
+            set_child(n, 0, root, rb);
+            BoxD none;
+            set_child(n, 1, leaf_link(LEAF_NONE, 0, 0), none);
+            nodes[0] = n;
+        }
+        return true;
+    }
+
+  private:
+    const hnm_scene_desc* d_;
+    std::vector<uint32_t> mesh_tri_base_;
+
+    static int32_t leaf_link(int kind, uint32_t count, uint32_t first) { return ~(int32_t)(((uint32_t)kind << 29) | (count << 26) | first); }
+
+    void collect_top(uint32_t node, std::vector<uint32_t>& order) {
+        const hnm_bvh_node& n = d_->top_nodes[node];
+        if (n.child0 < 0) {
+            for (uint32_t k = 0; k < n.count; k++) order.push_back(d_->top_indices[n.first + k]);
+        } else {
+            collect_top((uint32_t)n.child0, order);
+            collect_top((uint32_t)n.child1, order);
+        }
+    }
+    BoxD element_box(const hnm_element& e) {
+        if (e.kind == HNM_ELEM_SPHERE) {  // src/scene.rs:82-87
+            double mn[3] = {e.a.x - e.radius, e.a.y - e.radius, e.a.z - e.radius};
+            double mx[3] = {e.a.x + e.radius, e.a.y + e.radius, e.a.z + e.radius};
+            return box_of(mn, mx);
+        }
+        if (e.kind == HNM_ELEM_CUBOID) {
+            double mn[3] = {e.a.x, e.a.y, e.a.z}, mx[3] = {e.b.x, e.b.y, e.b.z};
+            return box_of(mn, mx);
+        }
+        const hnm_bvh_node& r = d_->mesh_nodes[d_->meshes[e.mesh].node_offset];
+        return box_of(r.aabb_min, r.aabb_max);
+    }
+    void set_child(DNode& n, int which, int32_t link, const BoxD& b) {
+        float lo[3], hi[3];
+        for (int k = 0; k < 3; k++) {
+            if (b.empty) { lo[k] = NAN; hi[k] = NAN; }  // NaN box: every comparison fails, never entered
+            else { lo[k] = f32_down(b.lo[k] - pad); hi[k] = f32_up(b.hi[k] + pad); }
+        }
+        if (which == 0) {
+            n.lo0x = lo[0]; n.lo0y = lo[1]; n.lo0z = lo[2]; n.hi0x = hi[0]; n.hi0y = hi[1]; n.hi0z = hi[2];
+            n.c0 = link;
+        } else {
+            n.lo1x = lo[0]; n.lo1y = lo[1]; n.lo1z = lo[2]; n.hi1x = hi[0]; n.hi1y = hi[1]; n.hi1z = hi[2];
+            n.c1 = link;
+        }
+    }
+    int32_t make_inner(int32_t l0, const BoxD& b0, int32_t l1, const BoxD& b1, int32_t slot = -1) {
+        DNode n;
+        memset(&n, 0, sizeof(n));
+        set_child(n, 0, l0, b0);
+        set_child(n, 1, l1, b1);
+        if (slot < 0) { nodes.push_back(n); return (int32_t)nodes.size() - 1; }
+        nodes[slot] = n;
+        return slot;
+    }
+    // a run of leaf-order triangles [first, first+count) -> leaf link (count <= 7) or a small subtree
+    int32_t tri_run(uint32_t first, uint32_t count, const BoxD& box) {
+        if (count == 0) return leaf_link(LEAF_NONE, 0, 0);
+        if (count <= 7) return leaf_link(LEAF_TRI, count, first);
+        uint32_t h = count / 2;
+        int32_t a = tri_run(first, h, box), b = tri_run(first + h, count - h, box);
+        return make_inner(a, box, b, box);
+    }
+    int32_t build_mesh(const hnm_mesh& m, uint32_t base, uint32_t rel, BoxD& out) {
+        const hnm_bvh_node& n = d_->mesh_nodes[m.node_offset + rel];
+        out = box_of(n.aabb_min, n.aabb_max);
+        if (n.child0 < 0) return tri_run(base + n.first, n.count, out);
+        int32_t slot = (int32_t)nodes.size();
+        nodes.push_back(DNode{});
+        BoxD b0, b1;
+        int32_t l0 = build_mesh(m, base, (uint32_t)n.child0, b0);
+        int32_t l1 = build_mesh(m, base, (uint32_t)n.child1, b1);
+        return make_inner(l0, b0, l1, b1, slot);
+    }
+    int32_t element_ref(uint32_t el, BoxD& out) {
+        const hnm_element& e = d_->elements[el];
+        if (e.kind == HNM_ELEM_MESH) return build_mesh(d_->meshes[e.mesh], mesh_tri_base_[e.mesh], 0, out);
+        out = element_box(e);
+        return leaf_link(e.kind == HNM_ELEM_SPHERE ? LEAF_SPHERE : LEAF_CUBOID, 1, el);
+    }
+    int32_t combine(const uint32_t* els, uint32_t count, BoxD& out) {
+        if (count == 0) { out = BoxD(); return leaf_link(LEAF_NONE, 0, 0); }
+        if (count == 1) return element_ref(els[0], out);
+        uint32_t h = count / 2;
+        BoxD b0, b1;
+        int32_t l0 = combine(els, h, b0), l1 = combine(els + h, count - h, b1);
+        out = BoxD();
+        out.grow(b0); out.grow(b1);
+        return make_inner(l0, b0, l1, b1);
+    }
+    int32_t build_top(uint32_t node, BoxD& out) {
+        const hnm_bvh_node& n = d_->top_nodes[node];
+        if (n.child0 < 0) return combine(d_->top_indices + n.first, n.count, out);
+        BoxD b0, b1;
+        int32_t l0 = build_top((uint32_t)n.child0, b0), l1 = build_top((uint32_t)n.child1, b1);
+        out = BoxD();
+        out.grow(b0); out.grow(b1);
+        return make_inner(l0, b0, l1, b1);
+    }
+};
+
+template <typename T>
+inline int upload(hnm_scene* s, const std::vector<T>& v, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    HNM_CUDA(cudaMalloc(&p, bytes));
+    s->allocs.push_back(p);
+    if (!v.empty()) HNM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return 0;
+}
+
+inline void scene_free(hnm_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (auto t : s->texs) cudaDestroyTextureObject(t);
+    for (auto a : s->arrays) cudaFreeArray(a);
+    for (auto p : s->allocs) cudaFree(p);
+    delete s;
+}
+
+inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out) {
+    if (!out) return set_error(HNM_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    SceneBuilder b(desc);
+    if (!b.validate()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    if (!b.build()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    HNM_CUDA(cudaSetDevice(device));
+    hnm_scene* s = new hnm_scene();
+    s->device = device;
+    s->config = desc->config;
+    memset(&s->d, 0, sizeof(s->d));
+    int rc = 0;
+    auto bail = [&](int code) { scene_free(s); return code; };
+    if ((rc = upload(s, b.nodes, &s->d.nodes))) return bail(rc);
+    if ((rc = upload(s, b.tris, &s->d.tris))) return bail(rc);
+    if ((rc = upload(s, b.tri_elem, &s->d.tri_elem))) return bail(rc);
+    if ((rc = upload(s, b.tri_face, &s->d.tri_face))) return bail(rc);
+    std::vector<DElement> els(desc->num_elements);
+    s->elem_surface.resize(desc->num_elements);
+    for (uint32_t i = 0; i < desc->num_elements; i++) {
+        const hnm_element& e = desc->elements[i];
+        DElement& de = els[i];
+        memset(&de, 0, sizeof(de));
+        de.ax = e.a.x; de.ay = e.a.y; de.az = e.a.z; de.bx = e.b.x; de.by = e.b.y; de.bz = e.b.z;
+        de.radius = e.radius; de.kind = e.kind; de.material = e.material; de.seq = b.elem_seq[i]; de.mesh = e.mesh;
+        s->elem_surface[i] = desc->materials[e.material].surface;
+    }
+    if ((rc = upload(s, els, &s->d.elements))) return bail(rc);
+    std::vector<DMaterial> mats(desc->num_materials);
+    for (uint32_t i = 0; i < desc->num_materials; i++) {
+        const hnm_material& m = desc->materials[i];
+        auto tex = [](const hnm_texture& t) { DTexture d; d.r = t.color.x; d.g = t.color.y; d.b = t.color.z; d.image = t.image < 0 ? -1 : t.image; d._pad = 0; return d; };
+        mats[i].albedo = tex(m.albedo); mats[i].emission = tex(m.emission); mats[i].roughness = tex(m.roughness);
+        mats[i].param = m.param; mats[i].surface = m.surface;
+        mats[i].has_image = (m.albedo.image >= 0 || m.emission.image >= 0 || m.roughness.image >= 0) ? 1 : 0;
+    }
+    if ((rc = upload(s, mats, &s->d.materials))) return bail(rc);
+    std::vector<DImage> imgs(desc->num_images);
+    for (uint32_t i = 0; i < desc->num_images; i++) {
+        const hnm_image& im = desc->images[i];
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        cudaError_t e = cudaMallocArray(&arr, &cd, im.width, im.height);
+        if (e != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("cudaMallocArray: ") + cudaGetErrorString(e)); return bail(HNM_ERR_CUDA); }
+        s->arrays.push_back(arr);
+        e = cudaMemcpy2DToArray(arr, 0, 0, im.rgba, (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("cudaMemcpy2DToArray: ") + cudaGetErrorString(e)); return bail(HNM_ERR_CUDA); }
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof(rd));
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td;
+        memset(&td, 0, sizeof(td));
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;       // exact texels; the reference's f64 bilinear is done in the kernel
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+        if (e != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("cudaCreateTextureObject: ") + cudaGetErrorString(e)); return bail(HNM_ERR_CUDA); }
+        s->texs.push_back(tex);
+        imgs[i].tex = tex; imgs[i].width = im.width; imgs[i].height = im.height;
+    }
+    if ((rc = upload(s, imgs, &s->d.images))) return bail(rc);
+    std::vector<uint32_t> em(desc->emissions, desc->emissions + desc->num_emissions);
+    if ((rc = upload(s, em, &s->d.emissions))) return bail(rc);
+    s->d.num_emissions = desc->num_emissions;
+    s->d.num_elements = desc->num_elements;
+    for (int k = 0; k < 6; k++) s->d.skybox_images[k] = desc->skybox_images[k];
+    s->d.sky_r = desc->skybox_intensity.x; s->d.sky_g = desc->skybox_intensity.y; s->d.sky_b = desc->skybox_intensity.z;
+    s->d.eps = desc->config.eps; s->d.offset = desc->config.offset; s->d.inf = desc->config.inf; s->d.gamma = desc->config.gamma_factor;
+    s->d.bounce_limit = desc->config.bounce_limit; s->d.supersampling = desc->config.supersampling;
+    double R = 0.0;
+    for (int k = 0; k < 3; k++) {
+        s->d.bounds_lo[k] = b.bounds.empty ? 0.0 : b.bounds.lo[k] - b.pad;
+        s->d.bounds_hi[k] = b.bounds.empty ? 0.0 : b.bounds.hi[k] + b.pad;
+        R = std::fmax(R, std::fmax(std::fabs(s->d.bounds_lo[k]), std::fabs(s->d.bounds_hi[k])));
+    }
+    s->d.far_limit = (float)(4.0 * R);
+    s->num_nodes = (uint32_t)b.nodes.size(); s->num_tris = (uint32_t)b.tris.size();
+    s->num_elements = desc->num_elements; s->num_emissions = desc->num_emissions;
+    *out = s;
+    return 0;
+}
+
+}  // namespace hnm
+#endif
