@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- Msamples/s of the radiance loop on the rtcamp6 scene at 1920x1080 (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path on the host cores
+
+sample = one camera path = one `PathTracingRenderer::calc_pixel` call (src/renderer.rs:163).
+step   = PASSES_PER_STEP passes of the pass loop (src/renderer.rs:32-38) over the whole image; the job is
+         K steps (default 16 x 16 = 256 passes = BASELINE config 2) followed by ONE all-gather (N > 1) and one
+         resolve (`update_imgbuf`), all inside the timed region.
+value  = samples of the whole job / device time (CUDA events on the renderer's stream, max over ranks); the
+         scene is resident in HBM when the timed region starts.
+e2e    = the same job through the reference-facing call PathTracingRenderer.render(scene, camera, imgbuf)
+         with HOST buffers: scene upload from host memory, passes, a progress image resolved and copied
+         back to the host every step, wall clock.
+N > 1  : one process per GPU (torchrun), interleaved row tiles, fixed total work -> "strong" scaling.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 1920, 1080
+SCENE = "rtcamp6"
+PASSES_PER_STEP = 16
+METRIC = "Msamples/sec (rtcamp6 scene, 1920x1080)"
+UNIT = "Msamples/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(n)
+        load = [s for s in sm if s > 0.5 * (max(mx) if mx else 1)] or sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_reference_run(oracle, scene, hr, steps, warmup, tile_stride=4):
+    """The reference's CPU path (oracle port, glibc libm, OpenMP over pixels like rayon's par_iter_mut) on a bounded
+    sample of the same workload: one pass over every `tile_stride`-th 8-row tile of the 1920x1080 image per step."""
+    import numpy as np
+    rows = [(y, min(y + 8, HEIGHT)) for y in range(0, HEIGHT, 8 * tile_stride)]
+    nrows = sum(b - a for a, b in rows)
+    accum = np.zeros((HEIGHT, WIDTH, 3), np.float64)
+
+    def one_step(sampling):
+        for a, b in rows:
+            oracle.render(scene, WIDTH, HEIGHT, hr.MODE_PATHTRACING, sampling, 1, accum=accum, rows=(a, b), counters=False)
+
+    for i in range(warmup):
+        one_step(1 + i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        one_step(1 + warmup + i)
+    dt = time.perf_counter() - t0
+    samples = nrows * WIDTH * 4 * steps
+    sample_desc = "%d passes over every %dth 8-row tile of the %dx%d image (%d rows, %.2f Msamples per step)" % (
+        steps, tile_stride, WIDTH, HEIGHT, nrows, nrows * WIDTH * 4 / 1e6)
+    return samples / dt / 1e6, dt, sample_desc
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0  # rank 0 alone runs the CPU arm
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import hanamaru_renderer_b200 as hr
+    from oracle_ffi import Oracle  # the one other place bench.py may execute oracle/
+    oracle = Oracle("glibc")
+    scene = hr.build_scene(SCENE, hr.AssetStore.from_pack())
+    cores = os.cpu_count()
+    value, dt, sample = cpu_reference_run(oracle, scene, hr, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (in-repo rtcamp6 scene from assets/hanamaru_assets.hnmpack)",
+        "config": {"workload": "rtcamp6 default scene 1920x1080 (BASELINE config 2), CPU sample per step: see cpu_baseline.sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample + "; oracle/liboracle.so = f64 C++ restatement of the Rust hot path (the Rust "
+                                            "reference cannot be built here: no cargo/rustc), OpenMP on all host threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with torchrun (one process per GPU)")
+    import hanamaru_renderer_b200 as hr
+    from hanamaru_renderer_b200 import dist as hd
+    if hr.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback on the product path")
+    import torch
+    torch.cuda.set_device(local)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    assets = hr.AssetStore.from_pack()
+    scene = hr.build_scene(SCENE, assets)
+    dev = hr.DeviceScene(scene, local)
+    shard = (rank, world, hd.DEFAULT_TILE_ROWS) if use_dist else None
+    ctx = hr.RenderContext(dev, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
+    P = PASSES_PER_STEP
+    K, Wm = args.steps, args.warmup
+
+    # ---- warm-up (untimed) -----------------------------------------------------------------------------
+    for i in range(Wm):
+        ctx.render_passes(1 + i * P, P)
+    ctx.synchronize()
+    if use_dist:
+        hd.gather_and_resolve(ctx, Wm * P)
+    else:
+        ctx.resolve(max(Wm * P, 1))
+    ctx.clear()
+    ctx.synchronize()
+
+    # ---- timed region: K steps + one gather + one resolve, device clock -------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    t_wall0 = time.perf_counter()
+    ctx.mark(0)
+    for i in range(K):
+        ctx.render_passes(1 + i * P, P)
+    ctx.mark(1)
+    if use_dist:
+        img, _ = hd.gather_and_resolve(ctx, K * P)
+    else:
+        img = ctx.resolve(K * P)
+    ctx.mark(2)
+    ctx.synchronize()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    ms_passes = ctx.elapsed_ms(0, 1)
+    ms_total = ctx.elapsed_ms(0, 2)
+    counters = ctx.counters()
+    if use_dist:
+        t = torch.tensor([ms_total, ms_passes, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_passes, wall = t.tolist()
+        c = torch.tensor([counters["segments"], counters["shadow_rays"], counters["kernel_launches"], counters["paths"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        counters["segments"], counters["shadow_rays"], counters["kernel_launches"], counters["paths"] = c.tolist()
+    samples = WIDTH * HEIGHT * 4 * P * K
+    assert counters["paths"] == samples, (counters["paths"], samples)
+    value = samples / (ms_total * 1e-3) / 1e6
+    launches = counters["kernel_launches"]
+
+    # ---- per-kernel device time + roofline of the dominant kernel (separate short profiled run) ---------------
+    ctx.clear()
+    ctx.synchronize()
+    ctx.set_profiling(True)
+    prof_steps = min(K, 2)
+    for i in range(prof_steps):
+        ctx.render_passes(1 + i * P, P)
+    ctx.synchronize()
+    ktimes = ctx.kernel_times()
+    pc = ctx.counters()
+    ctx.set_profiling(False)
+    peak, peak_src = load_peaks()
+    roofline = None
+    kernel_share = {}
+    if ktimes:
+        tot = sum(v[0] for v in ktimes.values())
+        kernel_share = {k: round(v[0] / tot, 4) for k, v in ktimes.items()}
+        top = max(ktimes, key=lambda k: ktimes[k][0])
+        paths_p = pc["paths"]
+        seg, sh = pc["segments"], pc["shadow_rays"]
+        nee_events = sh / max(1, scene.desc.contents.num_emissions)
+        # algorithmic bytes (f64 records actually shipped; DESIGN.md section "records"):
+        #   extend   : read ray 48 + pid 4, write hit 32, write one queue entry 4            = 88 B / segment
+        #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17, L rmw 48,
+        #              write next ray 76 (only surviving paths; counted for all)                = 253 B / NEE event
+        #   isaac    : write 32-word tail 256 + ray 76 + L 24 + cursor 1                       = 357 B / path
+        per_unit = {"extend": (88.0, seg), "shade_nee": (253.0, nee_events), "isaac_raygen": (357.0, paths_p),
+                    "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p), "shade_delta": (253.0 - 48.0, seg - nee_events)}
+        if top in per_unit:
+            b, units = per_unit[top]
+            ms, nl = ktimes[top]
+            achieved = b * units / (ms * 1e-3) / 1e9
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tp):
+                try:
+                    traffic = json.load(open(tp)).get(top)
+                except Exception:
+                    traffic = None
+            roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": traffic, "peak_source": peak_src, "launches": nl, "avg_launch_ms": ms / nl,
+                        "algorithmic_bytes_per_unit": b, "units_per_launch": units / nl,
+                        "note": "latency/issue bound by design: scene (<= 70 MB) is L2 resident, HBM only carries the wavefront records"}
+
+    # ---- end-to-end through the reference-facing call, host buffers, wall clock -----------------------------
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        imgbuf = np.zeros((HEIGHT, WIDTH, 3), np.uint8)
+        scene_bytes = scene_host_bytes(scene)
+        t0 = time.perf_counter()
+        dev2 = hr.DeviceScene(scene, local)                       # H2D: the flat scene description (host arrays)
+        ctx2 = hr.RenderContext(dev2, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
+        for i in range(K):
+            ctx2.render_passes(1 + i * P, P)
+            if use_dist:
+                imgbuf[:], _ = hd.gather_and_resolve(ctx2, (i + 1) * P)   # progress image every step: NCCL gather + resolve + D2H
+            else:
+                ctx2.resolve((i + 1) * P, out=imgbuf)             # D2H: the resolved u8 image
+        ctx2.synchronize()
+        barrier()
+        dt = time.perf_counter() - t0
+        if use_dist:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = t.item()
+        ctx2.close()
+        dev2.close()
+        e2e = {"value": samples / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": scene_bytes // K, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
+               "seconds": dt, "includes": "scene upload from host memory (once), %d passes, a resolved progress image copied to the host every step" % (K * P)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from oracle_ffi import Oracle  # checker / baseline only -- never on the product path
+        v, dt, sample = cpu_reference_run(Oracle("glibc"), scene, hr, steps=6, warmup=1)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+               "sample": sample + "; f64 C++ restatement (oracle/), OpenMP on all host threads; the Rust reference cannot be built here"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (in-repo rtcamp6 scene from assets/hanamaru_assets.hnmpack; seeds fixed by the algorithm)",
+            "config": {"workload": "rtcamp6 default scene 1920x1080, %d passes x 4 spp (BASELINE config 2), GGX + NEE + IBL, f64 parity mode" % (K * P),
+                       "passes_per_step": P, "resolve": "one all-gather (N>1) + one update_imgbuf inside the timed region",
+                       "l2": "wavefront records per step (>= 4 GB at N=1) are far larger than L2; no explicit flush",
+                       "parallelism": "interleaved 8-row tiles over %d rank(s), no data-path collective" % world,
+                       "passes_in_flight": "auto" if not args.batch else args.batch},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu,
+            "detail": {"ms_passes": ms_passes, "ms_total": ms_total, "wall_s": wall,
+                       "segments_per_sample": counters["segments"] / samples, "shadow_rays_per_sample": counters["shadow_rays"] / samples,
+                       "Mrays_per_s": (counters["segments"] + counters["shadow_rays"]) / (ms_total * 1e-3) / 1e6,
+                       "kernel_time_share": kernel_share, "image_mean": float(np.asarray(img).mean())},
+        }
+        print(json.dumps(line))
+    ctx.close()
+    if use_dist:
+        dist.destroy_process_group()
+    return 0
+
+
+def scene_host_bytes(scene):
+    """Bytes of host memory hnm_scene_create reads (what crosses PCIe/NVLink-C2C in some form)."""
+    from hanamaru_renderer_b200 import _ffi
+    import ctypes as C
+    d = scene.desc.contents
+    n = d.num_elements * C.sizeof(_ffi.Element) + d.num_materials * C.sizeof(_ffi.Material) + d.num_vertices * 24 + d.num_faces * 12
+    n += (d.num_mesh_nodes + d.num_top_nodes) * C.sizeof(_ffi.BvhNode) + (d.num_mesh_indices + d.num_top_indices) * 4
+    for i in range(d.num_images):
+        n += d.images[i].width * d.images[i].height * 4
+    return int(n)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="passes in flight per wavefront (0 = auto)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    import __graft_entry__ as g
+    rank, world, _ = dist_env()
+    if rank == 0:
+        g.build_host()
+        g.build_core()
+        g.build_oracle()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -290,6 +290,14 @@ class RenderContext:
     def set_profiling(self, on):
         _check(_ffi.core().hnm_set_profiling(self._h, int(on)))
 
+    def mark(self, slot):
+        _check(_ffi.core().hnm_mark(self._h, slot))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        _check(_ffi.core().hnm_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
     def kernel_times(self):
         names = (C.c_char_p * 32)()
         ms = (C.c_float * 32)()

@@ -133,6 +133,8 @@ CORE_SYMBOLS = {
     "hnm_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "hnm_get_kernel_times": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hnm_set_profiling": (C.c_int, [_P, C.c_int]),
+    "hnm_mark": (C.c_int, [_P, C.c_uint32]),
+    "hnm_elapsed_ms": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "hnm_intersect_batch": (C.c_int, [_P, _P, C.c_uint32, _P]),
     "hnm_isaac64_batch": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint32, _P]),
     "hnm_material_sample_batch": (C.c_int, [C.c_int, _P, C.c_uint32, _P]),

@@ -463,6 +463,7 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce, int b
     const bool last_bounce = (uint32_t)bounce + 1 >= P.sc.bounce_limit;
     TraceStats st;
     st.nodes = 0; st.prims = 0;
+    uint32_t shadow_rays = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t n_round = (n + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce, int b
             if (some) {
                 D3 L = d3(P.L[0][pid], P.L[1][pid], P.L[2][pid]);
                 if (NEE) {
+                    shadow_rays += P.sc.num_emissions;
                     D3 nee = next_event_estimation<STATS>(P, random, cos_phi, sin_phi, res.origin, view, sp.normal, pm, &st);
                     L = L + thr * nee;  // src/renderer.rs:183
                 }
@@ -505,7 +507,10 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce, int b
         uint32_t q2 = queue_alloc(alive, &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
         if (alive) store_ray(P, buf ^ 1, q2, no, nd, nthr, pid);
     }
-    if (NEE && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[S_SHADOW], (unsigned long long)n * P.sc.num_emissions);
+    if (NEE) {
+        for (int o = 16; o > 0; o >>= 1) shadow_rays += __shfl_xor_sync(0xFFFFFFFFu, shadow_rays, o);
+        if ((threadIdx.x & 31) == 0 && shadow_rays) atomicAdd(&P.stats[S_SHADOW], (unsigned long long)shadow_rays);
+    }
     if (STATS && NEE) {
         atomicAdd(&P.stats[S_NODES], (unsigned long long)st.nodes);
         atomicAdd(&P.stats[S_PRIMS], (unsigned long long)st.prims);
@@ -777,6 +782,7 @@ struct hnm_renderer {
     uint64_t launches = 0;
     KernelTimer timer;
     int sm_count = 148;
+    cudaEvent_t marks[16] = {};
 };
 
 namespace {
@@ -862,6 +868,7 @@ void hnm_renderer_destroy(hnm_renderer* r) {
     if (r->stream) cudaStreamSynchronize(r->stream);
     r->timer.collect();
     for (auto p : r->allocs) cudaFree(p);
+    for (auto e : r->marks) if (e) cudaEventDestroy(e);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -1050,6 +1057,21 @@ int hnm_set_profiling(hnm_renderer* r, int enabled) {
     if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
     r->timer.reset();
     r->profiling = enabled != 0;
+    return 0;
+}
+int hnm_mark(hnm_renderer* r, uint32_t slot) {
+    if (!r || slot >= 16) return set_error(HNM_ERR_INVALID, "bad mark slot");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    if (!r->marks[slot]) HNM_CUDA(cudaEventCreate(&r->marks[slot]));
+    HNM_CUDA(cudaEventRecord(r->marks[slot], r->stream));
+    return 0;
+}
+int hnm_elapsed_ms(hnm_renderer* r, uint32_t a, uint32_t b, float* ms) {
+    if (!r || !ms || a >= 16 || b >= 16 || !r->marks[a] || !r->marks[b]) return set_error(HNM_ERR_INVALID, "bad mark slot");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    HNM_CUDA(cudaEventSynchronize(r->marks[a]));
+    HNM_CUDA(cudaEventSynchronize(r->marks[b]));
+    HNM_CUDA(cudaEventElapsedTime(ms, r->marks[a], r->marks[b]));
     return 0;
 }
 int hnm_get_kernel_times(hnm_renderer* r, uint32_t max, const char** names, float* ms, uint32_t* launches, uint32_t* n) {

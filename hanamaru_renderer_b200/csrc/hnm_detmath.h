@@ -332,6 +332,7 @@ HNM_HD double acos(double x) {
     // acos(|x|) = 2 asin(sqrt((1-|x|)/2))
     double z = (1.0 - ax) * 0.5;
     double s = sqrt_(z);
+    if (s == 0.0) return x > 0.0 ? 0.0 : HNM_PI_HI;  // acos(+-1)
     double c = fma_(-s, s, z) / (2.0 * s);  // sqrt residual
     double w = fma_(s, z * asin_r_(z), c);
     if (x > 0.0) return 2.0 * (s + w);

@@ -302,7 +302,10 @@ HNM_D D3 sample_nearest_screen(const DImage& im, uint32_t x, uint32_t y) {  // s
     uchar4 p = tex2D<uchar4>(im.tex, (float)x + 0.5f, (float)y + 0.5f);
     return d3((double)p.x / 255.0, (double)p.y / 255.0, (double)p.z / 255.0);  // src/color.rs:18-24
 }
-HNM_D D3 sample_bilinear(const DScene& sc, const DImage& im, double u, double v) {  // src/texture.rs:29-49
+// One out-of-line copy per module: (1) it is called from every shading kernel, and (2) ptxas 12.9 miscompiled an
+// inlined copy inside k_intersect_batch (blue channel of the 4-texel blend wrong; the out-of-line call is exact --
+// tests/test_gpu_parity.py::test_intersect_batch_matches_oracle pins it).
+__device__ __noinline__ D3 sample_bilinear(double gamma, DImage im, double u, double v) {  // src/texture.rs:29-49
     double x = u * (double)im.width;
     double y = v * (double)im.height;
     double x1 = floor(x), y1 = floor(y);
@@ -313,10 +316,10 @@ HNM_D D3 sample_bilinear(const DScene& sc, const DImage& im, double u, double v)
     D3 p22 = sample_nearest_screen(im, f64_as_u32(x2), f64_as_u32(y2));
     D3 g = (p11 * (x2 - x) * (y2 - y) + p21 * (x - x1) * (y2 - y) + p12 * (x2 - x) * (y - y1) + p22 * (x - x1) * (y - y1)) /
            ((x2 - x1) * (y2 - y1));
-    return d3(dm::pow(g.x, sc.gamma), dm::pow(g.y, sc.gamma), dm::pow(g.z, sc.gamma));  // gamma_to_linear
+    return d3(dm::pow(g.x, gamma), dm::pow(g.y, gamma), dm::pow(g.z, gamma));  // gamma_to_linear
 }
 HNM_D D3 texture_sample(const DScene& sc, const DTexture& t, double u, double v) {  // src/texture.rs:108-114
-    if (t.image >= 0) return sample_bilinear(sc, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
+    if (t.image >= 0) return sample_bilinear(sc.gamma, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
     return d3(t.r, t.g, t.b);
 }
 // src/scene.rs:295-319
@@ -335,7 +338,7 @@ HNM_D D3 skybox_sample(const DScene& sc, D3 direction) {
         else { face = 5; u = direction.x / direction.z; v = -direction.y / direction.z; }
     }
     // sample_bilinear_0center (src/texture.rs:22-26)
-    D3 c = sample_bilinear(sc, sc.images[sc.skybox_images[face]], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
+    D3 c = sample_bilinear(sc.gamma, sc.images[sc.skybox_images[face]], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
     return d3(sc.sky_r, sc.sky_g, sc.sky_b) * c;
 }
 

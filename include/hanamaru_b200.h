@@ -254,6 +254,10 @@ int hnm_get_counters(hnm_renderer* r, hnm_counters* out);
  * events on the renderer's stream); names are static strings. */
 int hnm_get_kernel_times(hnm_renderer* r, uint32_t max, const char** names, float* ms, uint32_t* launches, uint32_t* n);
 int hnm_set_profiling(hnm_renderer* r, int enabled);
+/* Device-side stopwatch on the renderer's own stream (torch.cuda.Event only sees torch's stream):
+ * hnm_mark records CUDA event `slot` (0..15); hnm_elapsed_ms synchronises on both and returns b - a. */
+int hnm_mark(hnm_renderer* r, uint32_t slot);
+int hnm_elapsed_ms(hnm_renderer* r, uint32_t slot_a, uint32_t slot_b, float* ms);
 
 /* ---- batch entry points (per-function parity) ---------- */
 

@@ -1,0 +1,206 @@
+"""CPU tests: the host-side mirror (OBJ loader, BVH builder, flattening), the asset pack, and the C-ABI
+library (loads, exports every declared symbol, struct layouts agree) -- no compute calls."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REFERENCE = "/root/reference"
+
+
+def test_obj_parser_follows_loader_rs(hr):
+    a = hr.AssetStore()
+    # split on single spaces, only v / f, quads -> (a,b,c),(a,c,d), 1-based, "i/j/k" takes i, CRLF stripped
+    a.put_obj_text("t.obj", "# c\r\nv 0 0 0\r\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf 1/1/1 2/2/2 3/3/3 4/4/4\nf 1 2 3\ng x\n")
+    v, f = a.obj_geometry("t.obj")
+    assert v.tolist() == [[0, 0, 0], [1, 0, 0], [1, 1, 0], [0, 1, 0]]
+    assert f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+    # double space after `v` makes the reference panic on parse::<f64>("") -- reported, not papered over
+    with pytest.raises(hr.HanamaruError):
+        a.put_obj_text("bad.obj", "v  0 0 0\n")
+
+
+def test_bvh_builder_properties(hr, get_scene):
+    """src/bvh.rs:107-201: leaf iff len/2 <= 2 (<= 5 faces), first child = first half, DFS pre-order, exact boxes."""
+    d = get_scene("rtcamp6").desc.contents
+    for mi in range(d.num_meshes):
+        m = d.meshes[mi]
+        seen = np.zeros(m.face_count, bool)
+        verts = np.ctypeslib.as_array(d.vertices, shape=(d.num_vertices, 3))[m.vertex_offset:m.vertex_offset + m.vertex_count]
+        faces = np.ctypeslib.as_array(d.faces, shape=(d.num_faces, 3))[m.face_offset:m.face_offset + m.face_count]
+
+        def walk(rel):
+            n = d.mesh_nodes[m.node_offset + rel]
+            if n.child0 < 0:
+                assert 1 <= n.count <= 5
+                idx = [d.mesh_indices[m.index_offset + n.first + k] for k in range(n.count)]
+                for i in idx:
+                    assert not seen[i]
+                    seen[i] = True
+                tri = verts[faces[idx].reshape(-1)]
+                assert np.array_equal(tri.min(0), np.array(n.aabb_min[:])) and np.array_equal(tri.max(0), np.array(n.aabb_max[:]))
+                return len(idx), tri.min(0), tri.max(0)
+            assert n.child0 == rel + 1 and n.child1 > n.child0
+            c0, lo0, hi0 = walk(n.child0)
+            c1, lo1, hi1 = walk(n.child1)
+            assert c0 == (c0 + c1) // 2 and c0 + c1 > 5          # split_off(len / 2): first child gets the first half
+            lo, hi = np.minimum(lo0, lo1), np.maximum(hi0, hi1)
+            assert np.array_equal(lo, np.array(n.aabb_min[:])) and np.array_equal(hi, np.array(n.aabb_max[:]))
+            return c0 + c1, lo, hi
+
+        total, _, _ = walk(0)
+        assert total == m.face_count and seen.all()
+    # top level: 11 elements -> root, leaf(5), inner, leaf(3), leaf(3)
+    kinds = [(n.child0 < 0, n.count) for n in (d.top_nodes[i] for i in range(d.num_top_nodes))]
+    assert kinds == [(False, 0), (True, 5), (False, 0), (True, 3), (True, 3)]
+    assert sorted(d.top_indices[i] for i in range(d.num_top_indices)) == list(range(11))
+
+
+def test_default_scene_authoring(hr, get_scene):
+    """src/main.rs:1020-1153 spot checks."""
+    s = get_scene("rtcamp6")
+    d, cam = s.desc.contents, s.camera.contents
+    theta = 2 * np.pi * 0.03
+    assert np.allclose(cam.eye.tuple(), (6.5 * np.sin(theta), 2.0, 6.5 * np.cos(theta)), rtol=0, atol=1e-15)
+    assert cam.lens_radius == 0.015 and cam.focus_distance == 5.0 and cam.lens_shape == 1
+    # Camera::new uses tan(v_fov) with the FULL fov as the half angle (src/camera.rs:48)
+    assert abs(np.linalg.norm(cam.plane_half_up.tuple()) - np.tan(np.radians(20.0)) * 5.0) < 1e-14
+    e0 = d.elements[0]
+    assert e0.kind == 0 and e0.radius == 0.2 and e0.a.tuple() == (-0.3, 0.7, 0.0)
+    m0 = d.materials[e0.material]
+    assert m0.emission.color.tuple() == (30.0, 20.0, 4.0) and m0.albedo.color.tuple() == (0.0, 0.0, 0.0)
+    assert [d.elements[i].kind for i in range(11)] == [0, 2, 2, 2, 1, 2, 2, 2, 2, 2, 2]
+    surf = [d.materials[d.elements[i].material].surface for i in range(5, 11)]
+    assert surf == [hr.SURFACE_REFRACTION, hr.SURFACE_GGX] * 3
+    rough = [d.materials[d.elements[i].material].roughness.color.x for i in range(5, 11)]
+    assert np.allclose(rough, [0.1, 0.05, 0.1, 0.15, 0.1, 0.25])
+    assert d.emissions[0] == 0 and d.num_emissions == 1
+    c = d.config
+    assert (c.eps, c.offset, c.inf, c.gamma_factor, c.supersampling, c.bounce_limit) == (1e-4, 1e-4, 1e100, 2.2, 2, 10)
+
+
+def test_other_scenes_build(hr, get_scene):
+    assert get_scene("bvh_heavy").counts()["triangles"] == 12294 + 55888 + 7200
+    assert get_scene("diamond").counts()["triangles"] == 7 * 94
+    assert get_scene("material_examples_pl").counts()["elements"] == 7
+    s = get_scene("simple_pl")
+    assert s.counts()["emissions"] == 2 and s.desc.contents.skybox_intensity.tuple() == (0.0, 0.0, 0.0)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
+def test_pack_matches_reference_assets(hr):
+    """The committed asset pack is exactly what the host builds from the reference checkout."""
+    pack = hr.AssetStore.from_pack()
+    ref = hr.AssetStore.from_reference(REFERENCE, ("rtcamp6",))
+    for p in hr.scene_asset_paths("bvh_heavy", images=False) + hr.scene_asset_paths("diamond", images=False):
+        v0, f0 = pack.obj_geometry(p)
+        v1, f1 = ref.obj_geometry(p)
+        assert np.array_equal(v0, v1) and np.array_equal(f0, f1), p
+    a, b = hr.build_scene("rtcamp6", pack), hr.build_scene("rtcamp6", ref)
+    da, db = a.desc.contents, b.desc.contents
+    assert a.counts() == b.counts()
+    va = np.ctypeslib.as_array(da.vertices, shape=(da.num_vertices * 3,))
+    vb = np.ctypeslib.as_array(db.vertices, shape=(db.num_vertices * 3,))
+    assert np.array_equal(va, vb)
+    for i in range(da.num_images):
+        ia, ib = da.images[i], db.images[i]
+        assert (ia.width, ia.height) == (ib.width, ib.height)
+        pa = np.ctypeslib.as_array(C.cast(ia.rgba, C.POINTER(C.c_uint8)), shape=(ia.height * ia.width * 4,))
+        pb = np.ctypeslib.as_array(C.cast(ib.rgba, C.POINTER(C.c_uint8)), shape=(ib.height * ib.width * 4,))
+        assert np.array_equal(pa, pb)
+
+
+# ---- the C ABI ---------------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hanamaru_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hnm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_abi_library_exports_every_declared_symbol(hr):
+    import __graft_entry__ as g
+    path = g.build_core()          # nvcc cross-compiles sm_100a without a GPU
+    lib = C.CDLL(path)             # loads without a GPU (no compute call is made)
+    declared = _declared_symbols()
+    assert len(declared) >= 24
+    for name in declared:
+        assert hasattr(lib, name), "missing export: " + name
+    from hanamaru_renderer_b200 import _ffi
+    assert sorted(_ffi.CORE_SYMBOLS) == declared, "ctypes table and header disagree"
+    lib.hnm_abi_version.restype = C.c_uint32
+    assert lib.hnm_abi_version() == _ffi.HNM_ABI_VERSION
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, out), name
+
+
+def test_abi_struct_layouts(hr):
+    """ctypes mirrors == the C compiler's layout of include/hanamaru_b200.h."""
+    from hanamaru_renderer_b200 import _ffi
+    names = {"hnm_vec3": _ffi.Vec3, "hnm_camera": _ffi.Camera, "hnm_texture": _ffi.Texture, "hnm_material": _ffi.Material,
+             "hnm_image": _ffi.Image, "hnm_element": _ffi.Element, "hnm_bvh_node": _ffi.BvhNode, "hnm_mesh": _ffi.Mesh,
+             "hnm_config": _ffi.Config, "hnm_scene_desc": _ffi.SceneDesc, "hnm_shard": _ffi.Shard, "hnm_counters": _ffi.Counters,
+             "hnm_ray": _ffi.Ray, "hnm_hit": _ffi.Hit}
+    src = '#include <stdio.h>\n#include "hanamaru_b200.h"\nint main(){\n' + "".join(
+        'printf("%s %%zu\\n", sizeof(%s));\n' % (n, n) for n in names) + (
+        'printf("off_config %zu\\n", offsetof(hnm_scene_desc, config));\n'
+        'printf("off_skybox %zu\\n", offsetof(hnm_scene_desc, skybox_images));\n return 0;}\n')
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "t.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(td, "t.c"), "-o", os.path.join(td, "t")])
+        out = dict(l.split() for l in subprocess.run([os.path.join(td, "t")], capture_output=True, text=True).stdout.splitlines())
+    for n, t in names.items():
+        assert int(out[n]) == C.sizeof(t), n
+    assert int(out["off_config"]) == _ffi.SceneDesc.config.offset
+    assert int(out["off_skybox"]) == _ffi.SceneDesc.skybox_images.offset
+
+
+def test_no_cpu_fallback_without_device(hr):
+    """Without a GPU every compute entry point fails loudly; nothing routes to the oracle."""
+    import __graft_entry__ as g
+    g.build_core()
+    if hr.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    assets = hr.AssetStore.from_pack()
+    scene = hr.build_scene("diamond", assets)
+    with pytest.raises(hr.HanamaruError):
+        hr.DeviceScene(scene, 0)
+    with pytest.raises(hr.HanamaruError):
+        hr.isaac64_batch([[1, 2, 3, 4]], 8)
+    # and the product package never imports the oracle
+    for root, _, files in os.walk(os.path.join(ROOT, "hanamaru_renderer_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert "liboracle" not in text and "oracle_ffi" not in text, f
+                assert not re.search(r'#include\s+"[^"]*oracle', text), f
+                assert not re.search(r"^\s*(import|from)\s+oracle", text, flags=re.M), f
+
+
+def test_scene_validation_rejects_malformed(hr, get_scene):
+    """hnm_scene_create validates before touching the device: malformed descriptions -> HNM_ERR_INVALID."""
+    import copy
+    from hanamaru_renderer_b200 import _ffi
+    import __graft_entry__ as g
+    g.build_core()
+    core = _ffi.core()
+    src = get_scene("diamond").desc.contents
+    bad = _ffi.SceneDesc()
+    C.memmove(C.byref(bad), C.byref(src), C.sizeof(bad))
+    bad.abi_version = 99
+    h = C.c_void_p()
+    assert core.hnm_scene_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert b"abi_version" in core.hnm_last_error()
+    C.memmove(C.byref(bad), C.byref(src), C.sizeof(bad))
+    bad.skybox_images[2] = 1000
+    assert core.hnm_scene_create(C.byref(bad), 0, C.byref(h)) == -1
+    C.memmove(C.byref(bad), C.byref(src), C.sizeof(bad))
+    bad.num_elements = 0
+    assert core.hnm_scene_create(C.byref(bad), 0, C.byref(h)) == -1
+    assert core.hnm_scene_create(None, 0, C.byref(h)) == -1
+    del copy
