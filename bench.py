@@ -178,7 +178,7 @@ def run_ours(args):
     dev = hr.DeviceScene(scene, local)
     shard = (rank, world, hd.DEFAULT_TILE_ROWS) if use_dist else None
     ctx = hr.RenderContext(dev, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
-    P = PASSES_PER_STEP
+    P = args.pps
     K, Wm = args.steps, args.warmup
 
     # ---- warm-up (untimed) -----------------------------------------------------------------------------
@@ -348,6 +348,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="passes in flight per wavefront (0 = auto)")
+    ap.add_argument("--pps", type=int, default=PASSES_PER_STEP, help="passes per step (profiling runs use a small value)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -91,7 +91,8 @@ class Shard(C.Structure):
 
 class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64),
-                ("rng_fallbacks", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("rng_fallbacks", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64)]
 
 
 class Ray(C.Structure):

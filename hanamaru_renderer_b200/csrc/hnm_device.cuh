@@ -107,21 +107,30 @@ HNM_D uint32_t leaf_count(int32_t link) { return ((uint32_t)(~link) >> 26) & 7u;
 HNM_D uint32_t leaf_first(int32_t link) { return (uint32_t)(~link) & 0x3FFFFFFu; }
 
 // triangle in leaf order: v0, edge1 = v1 - v0, edge2 = v2 - v0 (the reference's own subtractions, done once)
-struct DTri {
-    double v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+struct __align__(16) DTri {  // 80 bytes: five 16-byte loads
+    double v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z, _pad;
 };
+HNM_D DTri load_tri(const DTri* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3), e = __ldg(q + 4);
+    DTri t;
+    t.v0x = a.x; t.v0y = a.y; t.v0z = b.x; t.e1x = b.y; t.e1y = c.x; t.e1z = c.y; t.e2x = d.x; t.e2y = d.y; t.e2z = e.x; t._pad = 0.0;
+    return t;
+}
 
 struct DScene {
     const DNode* nodes;
     const DTri* tris;
+    const float4* trif;        // f32 copy for the conservative pre-test: 3 x float4 per triangle = v0, e1, e2, e1 x e2
+    float scene_r;             // max |coordinate| of the scene box (error bound of the f32 origin)
     const uint32_t* tri_elem;  // element id per triangle
     const uint32_t* tri_face;  // face index inside its mesh
     const DElement* elements;
     const DMaterial* materials;
     const DImage* images;
+    const DImage* sky_faces;  // px nx py ny pz nz (device memory: indexed at run time)
     const uint32_t* emissions;
     uint32_t num_emissions, num_elements;
-    int32_t skybox_images[6];
     double sky_r, sky_g, sky_b;
     double eps, offset, inf, gamma;
     uint32_t bounce_limit, supersampling;
@@ -271,13 +280,7 @@ HNM_D Hit trace(const DScene& sc, D3 o, D3 dir, TraceStats* st) {
             if (kind == LEAF_TRI) {
                 uint32_t cnt = leaf_count(cur);
                 for (uint32_t k = 0; k < cnt; k++) {
-                    const double2* tp = reinterpret_cast<const double2*>(sc.tris + (first + k));
-                    // 72 bytes = 4 x 16 B + 8 B; triangles are 8-byte aligned only, so use scalar loads
-                    const double* dp = reinterpret_cast<const double*>(tp);
-                    DTri tr;
-                    tr.v0x = __ldg(dp); tr.v0y = __ldg(dp + 1); tr.v0z = __ldg(dp + 2);
-                    tr.e1x = __ldg(dp + 3); tr.e1y = __ldg(dp + 4); tr.e1z = __ldg(dp + 5);
-                    tr.e2x = __ldg(dp + 6); tr.e2y = __ldg(dp + 7); tr.e2z = __ldg(dp + 8);
+                    DTri tr = load_tri(sc.tris + (first + k));
                     if (STATS) st->prims++;
                     tri_test(tr, first + k, o, dir, best);
                 }
@@ -338,7 +341,9 @@ HNM_D D3 skybox_sample(const DScene& sc, D3 direction) {
         else { face = 5; u = direction.x / direction.z; v = -direction.y / direction.z; }
     }
     // sample_bilinear_0center (src/texture.rs:22-26)
-    D3 c = sample_bilinear(sc.gamma, sc.images[sc.skybox_images[face]], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
+    // the six faces live in device memory: a run-time index into a kernel-PARAMETER array makes nvcc 12.9 spill the
+    // parameter struct to local memory, and the copy it generated in one kernel was wrong (blue intensity garbage)
+    D3 c = sample_bilinear(sc.gamma, sc.sky_faces[face], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
     return d3(sc.sky_r, sc.sky_g, sc.sky_b) * c;
 }
 

@@ -1,0 +1,738 @@
+// hnm_kernels.cuh -- the wavefront kernel set around k_trace (hnm_trace.cuh).
+//
+// One batch of passes of PathTracingRenderer (src/renderer.rs:148-203):
+//   k_isaac_raygen   ISAAC-64 seeding per path (rand 0.4 StdRng; 2 KB of state per path in shared memory,
+//                    112 paths per CTA) + thin-lens camera ray (src/camera.rs:66-96)
+//   k_rng_overflow   exact slow path for the (rare) paths whose lens rejection loop outruns the stored
+//                    tail of the random stream
+//   per bounce b = 1 .. bounce_limit-1:
+//     k_trace        job 0: camera-path rays of bounce b (hits classified into miss / delta / NEE queues)
+//                    job 1: the NEE shadow rays of bounce b-1
+//     k_nee_resolve  (b-1) visibility test + light contribution (src/renderer.rs:282-291), radiance update
+//     k_shade_miss   Skybox::sample (src/scene.rs:295-319), radiance update, path ends
+//     k_shade_surf   material resolve, BSDF sample, throughput update, compaction into the next ray queue;
+//                    Diffuse / GGX hits also emit one shadow ray per emitter (src/renderer.rs:269-281)
+//   k_trace + k_nee_resolve for the last bounce's shadow rays
+//   k_accumulate     per pixel: sum of the sub-pixel paths in the reference's order, += into the f64
+//                    accumulation buffer (src/renderer.rs:37,56)
+// Resolve (src/renderer.rs:64-90): k_tonemap_gamma -> k_bilateral -> k_quantise.
+// Queue sizes live in device memory; a batch is enqueued without any host synchronisation.
+#ifndef HNM_KERNELS_CUH
+#define HNM_KERNELS_CUH
+
+#include "hnm_device.cuh"
+#include "hnm_trace.cuh"
+
+namespace hnm {
+
+constexpr int RNG_TAIL = HNM_RNG_TAIL;  // u64 outputs kept per path
+constexpr int ISAAC_THREADS = 112;      // 112 x 2 KB = 224 KB of the 227 KB a CTA may use
+constexpr int MAX_BOUNCE = 64;
+
+// counters[]: per bounce b (1-origin) eight slots
+enum { C_RAY = 0, C_MISS = 1, C_DELTA = 2, C_NEE = 3, C_EVENTS = 4, C_SHADOW = 5, C_WORK = 6, C_STRIDE = 8 };
+constexpr int OVF_COUNTER = (MAX_BOUNCE + 2) * C_STRIDE;
+constexpr int NUM_COUNTERS = OVF_COUNTER + 8;
+// stats[] (u64)
+enum { S_PATHS = 0, S_SEGMENTS = 1, S_SHADOW = 2, S_RNG_FALLBACK = 3, S_NODES = 4, S_PRIMS = 5, S_COUNT = 8 };
+
+struct RParams {
+    DScene sc;
+    hnm_camera cam;
+    uint32_t W, H, ss, spp;
+    uint32_t npix;        // owned pixels that exist in the image
+    uint32_t real_rows;   // owned rows that exist
+    uint32_t rank, nranks, tile_rows;
+    uint32_t batch, sampling_first;
+    uint32_t N;           // paths in this batch = batch * npix * spp
+    uint32_t cap;         // allocated paths
+    int mode;
+    int tail_k;           // usable words of the RNG tail (<= RNG_TAIL; smaller only in tests)
+    // camera-path rays, double buffered by bounce parity (queue order)
+    // (`rin` = the queue this bounce reads, `rout` = the queue it writes; the host swaps them per launch so that no
+    // kernel indexes a parameter array at run time)
+    double* rin[6]; double* tin[3]; uint32_t* pin;
+    double* rout[6]; double* tout[3]; uint32_t* pout;
+    // per path (slot order)
+    double* L[3];
+    uint8_t* cursor;
+    uint64_t* tail;       // [RNG_TAIL][cap]
+    // hits of the current bounce (queue order)
+    double* hit_t; double* hit_u; double* hit_v; uint2* hit_id;
+    uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee; uint32_t* q_ovf;
+    // NEE events of the current bounce and their shadow rays (num_emissions per event, event-major)
+    double* ev_thr[3]; double* ev_albedo[3]; double* ev_emission[3]; uint32_t* ev_pid;
+    double* sray[6]; double* s_pos[3]; double* s_bsdf; double* s_g;
+    double* sh_t; double* sh_u; double* sh_v; uint2* sh_id;
+    uint32_t* counters;
+    unsigned long long* stats;
+    double* accum;        // [padded_rows * W * 3]
+};
+
+__host__ __device__ inline uint32_t local_to_global_row_h(uint32_t lr, uint32_t rank, uint32_t nranks, uint32_t tile_rows) {
+    uint32_t lt = lr / tile_rows;
+    return (lt * nranks + rank) * tile_rows + (lr % tile_rows);
+}
+
+// path p -> pass, local pixel, sub-pixel; and the normalized coordinate of src/renderer.rs:34-36,51-54
+struct PathCoord {
+    uint32_t pass, pix, sub, x, y;
+    double ncx, ncy;
+};
+HNM_D PathCoord path_coord(const RParams& P, uint32_t p) {
+    PathCoord c;
+    c.sub = p % P.spp;
+    uint32_t r = p / P.spp;
+    c.pix = r % P.npix;
+    c.pass = r / P.npix;
+    uint32_t lr = c.pix / P.W;
+    c.x = c.pix - lr * P.W;
+    c.y = local_to_global_row_h(lr, P.rank, P.nranks, P.tile_rows);
+    uint32_t sx = c.sub % P.ss, sy = c.sub / P.ss;
+    double fx = (double)c.x, fy = (double)(P.H - c.y);  // frag_coord = (x, height - y)
+    double offx = (double)sx / (double)P.ss - 0.5, offy = (double)sy / (double)P.ss - 0.5;
+    double rx = (double)P.W, ry = (double)P.H;
+    double m = fmin(rx, ry);
+    c.ncx = ((fx + offx) * 2.0 - rx) / m;
+    c.ncy = ((fy + offy) * 2.0 - ry) / m;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------ ISAAC-64
+// rand 0.4.3 src/prng/isaac64.rs (third-party, restated; pinned by rand's own KATs in the tests).
+#define ISAAC_MIX(a, b, c, d, e, f, g, h) \
+    a -= e; f ^= h >> 9;  h += a;         \
+    b -= f; g ^= a << 9;  a += b;         \
+    c -= g; h ^= b >> 23; b += c;         \
+    d -= h; a ^= c << 15; c += d;         \
+    e -= a; b ^= d >> 14; d += e;         \
+    f -= b; c ^= e << 20; e += f;         \
+    g -= c; d ^= f >> 17; f += g;         \
+    h -= d; e ^= g << 14; g += h;
+
+// `mem` is this thread's column of a [256][T] u64 array (shared memory: conflict-free for any per-lane
+// index because the bank depends only on the lane).  Outputs rsl[i] are handed to `sink`.
+template <int T, typename Sink>
+__device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, Sink sink) {
+#define MEM(i) mem[(i) * T]
+    uint64_t a, b, c, d, e, f, g, h;
+    a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) { ISAAC_MIX(a, b, c, d, e, f, g, h) }
+    // first pass mixes in rsl = [s0 s1 s2 s3 0 0 ...]
+    a += s0; b += s1; c += s2; d += s3;
+#pragma unroll 1
+    for (int i = 0; i < 256; i += 8) {
+        ISAAC_MIX(a, b, c, d, e, f, g, h)
+        MEM(i) = a; MEM(i + 1) = b; MEM(i + 2) = c; MEM(i + 3) = d;
+        MEM(i + 4) = e; MEM(i + 5) = f; MEM(i + 6) = g; MEM(i + 7) = h;
+    }
+    // second pass mixes in mem
+#pragma unroll 1
+    for (int i = 0; i < 256; i += 8) {
+        a += MEM(i); b += MEM(i + 1); c += MEM(i + 2); d += MEM(i + 3);
+        e += MEM(i + 4); f += MEM(i + 5); g += MEM(i + 6); h += MEM(i + 7);
+        ISAAC_MIX(a, b, c, d, e, f, g, h)
+        MEM(i) = a; MEM(i + 1) = b; MEM(i + 2) = c; MEM(i + 3) = d;
+        MEM(i + 4) = e; MEM(i + 5) = f; MEM(i + 6) = g; MEM(i + 7) = h;
+    }
+    // isaac64(): a = 0, b = 0, c = 1  ->  aa = 0, bb = 1
+    uint64_t aa = 0, bb = 1;
+#define ISAAC_STEP(mixexpr, i, i2)                              \
+    {                                                           \
+        uint64_t x = MEM(i);                                    \
+        aa = (mixexpr) + MEM(i2);                               \
+        uint64_t y = MEM(((uint32_t)x >> 3) & 255u) + aa + bb;  \
+        MEM(i) = y;                                             \
+        bb = MEM(((uint32_t)y >> 11) & 255u) + x;               \
+        sink(i, bb);                                            \
+    }
+#pragma unroll 1
+    for (int base = 0; base < 128; base += 4) {
+        ISAAC_STEP(~(aa ^ (aa << 21)), base, base + 128)
+        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base + 129)
+        ISAAC_STEP(aa ^ (aa << 12), base + 2, base + 130)
+        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base + 131)
+    }
+#pragma unroll 1
+    for (int base = 128; base < 256; base += 4) {
+        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128)
+        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127)
+        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126)
+        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125)
+    }
+#undef ISAAC_STEP
+#undef MEM
+}
+
+// Complete generator with refill, state in local memory: the exact slow path.
+struct IsaacFull {
+    uint64_t rsl[256], mem[256];
+    uint64_t a, b, c;
+    uint32_t cnt;
+    __device__ void round() {
+        c += 1;
+        uint64_t aa = a, bb = b + c;
+        for (int half = 0; half < 2; half++) {
+            int mr = half == 0 ? 0 : 128, m2 = half == 0 ? 128 : 0;
+            for (int base = 0; base < 128; base += 4) {
+                for (int j = 0; j < 4; j++) {
+                    uint64_t mixv = j == 0 ? ~(aa ^ (aa << 21)) : j == 1 ? (aa ^ (aa >> 5)) : j == 2 ? (aa ^ (aa << 12)) : (aa ^ (aa >> 33));
+                    uint64_t x = mem[base + j + mr];
+                    aa = mixv + mem[base + j + m2];
+                    uint64_t y = mem[(x >> 3) & 255] + aa + bb;
+                    mem[base + j + mr] = y;
+                    bb = mem[(y >> 11) & 255] + x;
+                    rsl[base + j + mr] = bb;
+                }
+            }
+        }
+        a = aa; b = bb; cnt = 256;
+    }
+    __device__ void seed(uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3) {
+        for (int i = 0; i < 256; i++) rsl[i] = 0;
+        rsl[0] = s0; rsl[1] = s1; rsl[2] = s2; rsl[3] = s3;
+        a = b = c = 0;
+        uint64_t a_, b_, c_, d_, e_, f_, g_, h_;
+        a_ = b_ = c_ = d_ = e_ = f_ = g_ = h_ = 0x9e3779b97f4a7c13ull;
+        for (int i = 0; i < 4; i++) { ISAAC_MIX(a_, b_, c_, d_, e_, f_, g_, h_) }
+        for (int pass = 0; pass < 2; pass++) {
+            const uint64_t* src = pass == 0 ? rsl : mem;
+            for (int i = 0; i < 256; i += 8) {
+                a_ += src[i]; b_ += src[i + 1]; c_ += src[i + 2]; d_ += src[i + 3];
+                e_ += src[i + 4]; f_ += src[i + 5]; g_ += src[i + 6]; h_ += src[i + 7];
+                ISAAC_MIX(a_, b_, c_, d_, e_, f_, g_, h_)
+                mem[i] = a_; mem[i + 1] = b_; mem[i + 2] = c_; mem[i + 3] = d_;
+                mem[i + 4] = e_; mem[i + 5] = f_; mem[i + 6] = g_; mem[i + 7] = h_;
+            }
+        }
+        round();
+    }
+    __device__ uint64_t next_u64() {
+        if (cnt == 0) round();
+        cnt -= 1;
+        return rsl[cnt & 255];
+    }
+};
+
+HNM_D void path_seed(const PathCoord& c, uint32_t sampling, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
+    // src/renderer.rs:165-167
+    s0 = 8700304ull;
+    s1 = (uint64_t)sampling;
+    s2 = f64_as_u64((4.0 + c.ncx) * 100870.0);
+    s3 = f64_as_u64((4.0 + c.ncy) * 100304.0);
+}
+
+// thin-lens ray from an accepted lens sample (src/camera.rs:83-96)
+HNM_D void lens_ray(const hnm_camera& cm, double ncx, double ncy, double sqx, double sqy, D3& origin, D3& direction) {
+    double lx = sqx * cm.lens_radius, ly = sqy * cm.lens_radius;
+    D3 lens_pos = d3(cm.right) * lx + d3(cm.up) * ly;
+    origin = d3(cm.eye) + lens_pos;
+    direction = normalize(ncx * d3(cm.plane_half_right) + ncy * d3(cm.plane_half_up) + cm.focus_distance * d3(cm.forward) - lens_pos);
+}
+
+HNM_D void store_ray(const RParams& P, uint32_t q, D3 o, D3 d, D3 t, uint32_t pid) {
+    P.rout[0][q] = o.x; P.rout[1][q] = o.y; P.rout[2][q] = o.z;
+    P.rout[3][q] = d.x; P.rout[4][q] = d.y; P.rout[5][q] = d.z;
+    P.tout[0][q] = t.x; P.tout[1][q] = t.y; P.tout[2][q] = t.z;
+    P.pout[q] = pid;
+}
+
+__global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_raygen(RParams P) {
+    extern __shared__ uint64_t smem_isaac[];
+    const int tid = threadIdx.x;
+    uint64_t* mem = smem_isaac + tid;
+    const uint32_t N = P.N, cap = P.cap;
+    for (uint32_t p = blockIdx.x * ISAAC_THREADS + tid; p < N; p += gridDim.x * ISAAC_THREADS) {
+        PathCoord c = path_coord(P, p);
+        uint64_t s0, s1, s2, s3;
+        path_seed(c, P.sampling_first + c.pass, s0, s1, s2, s3);
+        uint64_t* tail = P.tail + p;
+        // outputs are consumed from rsl[255] downwards: word j of the stream = rsl[255 - j]
+        isaac64_seed<ISAAC_THREADS>(mem, s0, s1, s2, s3, [&](int i, uint64_t v) {
+            if (i >= 256 - RNG_TAIL) tail[(size_t)(255 - i) * cap] = v;
+        });
+        // sample_on_lens (src/camera.rs:66-81): rejection loop over pairs of the stream
+        int cur = 0;
+        double sqx = 0.0, sqy = 0.0;
+        bool ok = false;
+        while (cur + 2 <= P.tail_k) {
+            double u = u64_to_f64(tail[(size_t)cur * cap]);
+            double v = u64_to_f64(tail[(size_t)(cur + 1) * cap]);
+            cur += 2;
+            sqx = 2.0 * u - 1.0;
+            sqy = 2.0 * v - 1.0;
+            if (P.cam.lens_shape == 0 || sqx * sqx + sqy * sqy < 1.0) { ok = true; break; }
+        }
+        P.L[0][p] = 0.0; P.L[1][p] = 0.0; P.L[2][p] = 0.0;
+        if (!ok || cur + 2 * (int)(P.sc.bounce_limit - 1) > P.tail_k) {
+            // the stored tail is too short for this path: exact slow path (k_rng_overflow fills the slot)
+            uint32_t slot = atomicAdd(&P.counters[OVF_COUNTER], 1u);
+            P.q_ovf[slot] = p;
+            continue;
+        }
+        D3 o, d;
+        lens_ray(P.cam, c.ncx, c.ncy, sqx, sqy, o, d);
+        store_ray(P, p, o, d, splat(1.0), p);
+        P.cursor[p] = (uint8_t)cur;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        P.counters[1 * C_STRIDE + C_RAY] = N;
+        atomicAdd(&P.stats[S_PATHS], (unsigned long long)N);
+    }
+}
+
+__global__ void k_rng_overflow(RParams P) {
+    uint32_t n = P.counters[OVF_COUNTER];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t p = P.q_ovf[i];
+        PathCoord c = path_coord(P, p);
+        uint64_t s0, s1, s2, s3;
+        path_seed(c, P.sampling_first + c.pass, s0, s1, s2, s3);
+        IsaacFull rng;
+        rng.seed(s0, s1, s2, s3);
+        double sqx, sqy;
+        for (;;) {
+            double u = u64_to_f64(rng.next_u64());
+            double v = u64_to_f64(rng.next_u64());
+            sqx = 2.0 * u - 1.0;
+            sqy = 2.0 * v - 1.0;
+            if (P.cam.lens_shape == 0 || sqx * sqx + sqy * sqy < 1.0) break;
+        }
+        // the per-bounce pairs follow; park them at the start of this path's tail
+        int need = 2 * (int)(P.sc.bounce_limit - 1);
+        for (int j = 0; j < need && j < RNG_TAIL; j++) P.tail[(size_t)j * P.cap + p] = rng.next_u64();
+        D3 o, d;
+        lens_ray(P.cam, c.ncx, c.ncy, sqx, sqy, o, d);
+        store_ray(P, p, o, d, splat(1.0), p);
+        P.cursor[p] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[S_RNG_FALLBACK], (unsigned long long)n);
+}
+
+// DebugRenderer: pinhole ray, no RNG (src/camera.rs:98-107, src/renderer.rs:117)
+__global__ void k_raygen_debug(RParams P) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P.N; p += gridDim.x * blockDim.x) {
+        PathCoord c = path_coord(P, p);
+        D3 o = d3(P.cam.eye);
+        D3 d = normalize(c.ncx * d3(P.cam.plane_half_right) + c.ncy * d3(P.cam.plane_half_up) + P.cam.focus_distance * d3(P.cam.forward));
+        store_ray(P, p, o, d, splat(1.0), p);
+        P.L[0][p] = 0.0; P.L[1][p] = 0.0; P.L[2][p] = 0.0;
+        P.cursor[p] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.counters[1 * C_STRIDE + C_RAY] = P.N;
+        atomicAdd(&P.stats[S_PATHS], (unsigned long long)P.N);
+    }
+}
+
+// slot in a compacted queue for every lane with `pred`; one atomic per warp
+HNM_D uint32_t queue_alloc(bool pred, uint32_t* counter) {
+    unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
+    if (mask == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+HNM_D D3 load_ray_o(const RParams& P, uint32_t q) { return d3(P.rin[0][q], P.rin[1][q], P.rin[2][q]); }
+HNM_D D3 load_ray_d(const RParams& P, uint32_t q) { return d3(P.rin[3][q], P.rin[4][q], P.rin[5][q]); }
+HNM_D D3 load_thr(const RParams& P, uint32_t q) { return d3(P.tin[0][q], P.tin[1][q], P.tin[2][q]); }
+
+// ------------------------------------------------------------------------------------ shade
+HNM_D Rand2 bounce_random(const RParams& P, uint32_t pid, int bounce) {
+    // `let random = rng.gen::<(f64, f64)>()` at the top of every bounce (src/renderer.rs:175)
+    size_t w = (size_t)P.cursor[pid] + 2u * (uint32_t)(bounce - 1);
+    Rand2 r;
+    r.r0 = u64_to_f64(P.tail[w * P.cap + pid]);
+    r.r1 = u64_to_f64(P.tail[(w + 1) * P.cap + pid]);
+    return r;
+}
+
+__global__ void __launch_bounds__(256) k_shade_miss(RParams P, int bounce) {
+    const uint32_t n = P.counters[bounce * C_STRIDE + C_MISS];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t q = P.q_miss[i];
+        uint32_t pid = P.pin[q];
+        D3 d = load_ray_d(P, q);
+        D3 thr = load_thr(P, q);
+        D3 emission = skybox_sample(P.sc, d);  // src/scene.rs:398
+        // accumulation += reflectance * emission (src/renderer.rs:196); the path ends (!hit, :199)
+        D3 L = d3(P.L[0][pid], P.L[1][pid], P.L[2][pid]);
+        L = L + thr * emission;
+        P.L[0][pid] = L.x; P.L[1][pid] = L.y; P.L[2][pid] = L.z;
+    }
+}
+
+// One surface interaction of PathTracingRenderer::calc_pixel (src/renderer.rs:176-199) for queue
+// `cls` (C_DELTA: Specular / Refraction / GGXRefraction, C_NEE: Diffuse / GGX).  For the NEE class the
+// light samples (Sphere::sample_on_surface, src/scene.rs:92-101) become shadow rays for the next k_trace
+// and the radiance update moves to k_nee_resolve, which keeps the reference's order
+// `accumulation += reflectance * nee` BEFORE `accumulation += reflectance * emission`.
+template <bool NEE>
+__global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce) {
+    const int cls = NEE ? C_NEE : C_DELTA;
+    const uint32_t n = P.counters[bounce * C_STRIDE + cls];
+    const uint32_t* queue = NEE ? P.q_nee : P.q_delta;
+    const bool last_bounce = (uint32_t)bounce + 1 >= P.sc.bounce_limit;
+    const uint32_t nl = P.sc.num_emissions;
+    uint32_t shadow_rays = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool alive = false, event = false;
+        D3 no = splat(0.0), nd = splat(0.0), nthr = splat(0.0), thr = splat(0.0), view = splat(0.0);
+        SurfacePoint sp;
+        PointMaterial pm;
+        Rand2 random;
+        double cos_phi = 1.0, sin_phi = 0.0;
+        uint32_t pid = 0;
+        if (i < n) {
+            uint32_t q = queue[i];
+            pid = P.pin[q];
+            D3 o = load_ray_o(P, q), d = load_ray_d(P, q);
+            thr = load_thr(P, q);
+            Hit h;
+            h.t = P.hit_t[q]; h.u = P.hit_u[q]; h.v = P.hit_v[q];
+            uint2 hid = P.hit_id[q];
+            h.kind = hid.x; h.id = hid.y;
+            uint32_t el = h.kind == LEAF_TRI ? P.sc.tri_elem[h.id] : h.id;
+            const DMaterial& dm_ = P.sc.materials[P.sc.elements[el].material];
+            sp = surface_point(P.sc, h, o, d, dm_.has_image != 0);
+            pm = resolve_material(P.sc, dm_, sp.u, sp.v);
+            random = bounce_random(P, pid, bounce);
+            if (pm.surface != HNM_SURFACE_SPECULAR && pm.surface != HNM_SURFACE_REFRACTION) dm::sincos(HNM_PI2 * random.r0, sin_phi, cos_phi);
+            view = -d;
+            SampleResult res;
+            bool some = material_sample(P.sc, pm, random, cos_phi, sin_phi, sp.position, view, sp.normal, res);
+            if (some) {
+                nthr = thr * (pm.albedo * res.reflectance);          // src/renderer.rs:197
+                alive = !all_zero(nthr) && !last_bounce;             // :199 and the loop bound :174
+                no = res.origin; nd = res.direction;
+                if (NEE) {
+                    event = true;
+                } else {
+                    D3 L = d3(P.L[0][pid], P.L[1][pid], P.L[2][pid]);
+                    L = L + thr * pm.emission;                       // :196
+                    P.L[0][pid] = L.x; P.L[1][pid] = L.y; P.L[2][pid] = L.z;
+                }
+            }
+            // None: `break` before the emission is added (src/renderer.rs:190-193)
+        }
+        uint32_t q2 = queue_alloc(alive, &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
+        if (alive) store_ray(P, q2, no, nd, nthr, pid);
+        if (NEE) {
+            uint32_t ev = queue_alloc(event, &P.counters[bounce * C_STRIDE + C_EVENTS]);
+            if (event) {
+                P.ev_thr[0][ev] = thr.x; P.ev_thr[1][ev] = thr.y; P.ev_thr[2][ev] = thr.z;
+                P.ev_albedo[0][ev] = pm.albedo.x; P.ev_albedo[1][ev] = pm.albedo.y; P.ev_albedo[2][ev] = pm.albedo.z;
+                P.ev_emission[0][ev] = pm.emission.x; P.ev_emission[1][ev] = pm.emission.y; P.ev_emission[2][ev] = pm.emission.z;
+                P.ev_pid[ev] = pid;
+                shadow_rays += nl;
+                // next_event_estimation (src/renderer.rs:275-281): position = result.ray.origin
+                for (uint32_t k = 0; k < nl; k++) {
+                    const DElement& e = P.sc.elements[P.sc.emissions[k]];
+                    // Sphere::sample_on_surface; theta = PI2 * random.0 is the phi of the BSDF sample
+                    double unit_z = 1.0 - 2.0 * random.r1;
+                    double a = __dsqrt_rn(1.0 - unit_z * unit_z);
+                    D3 s_normal = d3(a * cos_phi, a * sin_phi, unit_z);
+                    D3 s_position = d3(e.ax, e.ay, e.az) + (e.radius + P.sc.offset) * s_normal;
+                    D3 shadow_vec = s_position - no;
+                    D3 shadow_dir = normalize(shadow_vec);
+                    double dot_0 = fabs(dot(sp.normal, shadow_dir));
+                    double dot_l = fabs(dot(s_normal, shadow_dir));
+                    double distance_pow2 = dot(shadow_vec, shadow_vec);
+                    size_t s = (size_t)ev * nl + k;
+                    P.sray[0][s] = no.x; P.sray[1][s] = no.y; P.sray[2][s] = no.z;
+                    P.sray[3][s] = shadow_dir.x; P.sray[4][s] = shadow_dir.y; P.sray[5][s] = shadow_dir.z;
+                    P.s_pos[0][s] = s_position.x; P.s_pos[1][s] = s_position.y; P.s_pos[2][s] = s_position.z;
+                    P.s_g[s] = (dot_0 * dot_l) / distance_pow2;
+                    P.s_bsdf[s] = bsdf(pm, view, sp.normal, shadow_dir);
+                }
+            }
+        }
+    }
+    if (NEE) {
+        for (int o = 16; o > 0; o >>= 1) shadow_rays += __shfl_xor_sync(0xFFFFFFFFu, shadow_rays, o);
+        if ((threadIdx.x & 31) == 0 && shadow_rays) {
+            atomicAdd(&P.stats[S_SHADOW], (unsigned long long)shadow_rays);
+            atomicAdd(&P.counters[bounce * C_STRIDE + C_SHADOW], shadow_rays);
+        }
+    }
+}
+
+// src/renderer.rs:282-295 + :183,196 for the NEE events of one bounce, after their shadow rays were traced
+__global__ void __launch_bounds__(256) k_nee_resolve(RParams P, int bounce) {
+    const uint32_t n = P.counters[bounce * C_STRIDE + C_EVENTS];
+    const uint32_t nl = P.sc.num_emissions;
+    const DScene& sc = P.sc;
+    for (uint32_t ev = blockIdx.x * blockDim.x + threadIdx.x; ev < n; ev += gridDim.x * blockDim.x) {
+        D3 accumulation = splat(0.0);
+        for (uint32_t k = 0; k < nl; k++) {
+            size_t s = (size_t)ev * nl + k;
+            uint2 hid = P.sh_id[s];
+            if (hid.x == LEAF_NONE) continue;
+            Hit h;
+            h.t = P.sh_t[s]; h.u = P.sh_u[s]; h.v = P.sh_v[s]; h.kind = hid.x; h.id = hid.y;
+            D3 o = d3(P.sray[0][s], P.sray[1][s], P.sray[2][s]);
+            D3 d = d3(P.sray[3][s], P.sray[4][s], P.sray[5][s]);
+            D3 s_position = d3(P.s_pos[0][s], P.s_pos[1][s], P.s_pos[2][s]);
+            D3 hit_pos = o + d * h.t;
+            if (norm(hit_pos - s_position) < sc.offset * 4.0) {  // Vector3::approximately (src/vector.rs:89-91)
+                uint32_t el = h.kind == LEAF_TRI ? sc.tri_elem[h.id] : h.id;
+                const DMaterial& hm = sc.materials[sc.elements[el].material];
+                D3 emission;
+                if (hm.emission.image >= 0) {
+                    SurfacePoint sp = surface_point(sc, h, o, d, true);
+                    emission = texture_sample(sc, hm.emission, sp.u, sp.v);
+                } else {
+                    emission = d3(hm.emission.r, hm.emission.g, hm.emission.b);
+                }
+                const DElement& e = sc.elements[sc.emissions[k]];
+                double pdf = 1.0 / (4.0 * HNM_PI * e.radius * e.radius);
+                accumulation = accumulation + emission * P.s_bsdf[s] * P.s_g[s] / pdf;
+            }
+        }
+        D3 nee = accumulation * d3(P.ev_albedo[0][ev], P.ev_albedo[1][ev], P.ev_albedo[2][ev]);
+        D3 thr = d3(P.ev_thr[0][ev], P.ev_thr[1][ev], P.ev_thr[2][ev]);
+        D3 emission = d3(P.ev_emission[0][ev], P.ev_emission[1][ev], P.ev_emission[2][ev]);
+        uint32_t pid = P.ev_pid[ev];
+        D3 L = d3(P.L[0][pid], P.L[1][pid], P.L[2][pid]);
+        L = L + thr * nee;       // src/renderer.rs:183
+        L = L + thr * emission;  // :196
+        P.L[0][pid] = L.x; P.L[1][pid] = L.y; P.L[2][pid] = L.z;
+    }
+}
+
+// DebugRenderer::calc_pixel (src/renderer.rs:116-139)
+__global__ void __launch_bounds__(256) k_debug_shade(RParams P) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < P.N; q += gridDim.x * blockDim.x) {
+        D3 o = load_ray_o(P, q), d = load_ray_d(P, q);
+        Hit h;
+        h.t = P.hit_t[q]; h.u = P.hit_u[q]; h.v = P.hit_v[q];
+        uint2 hid = P.hit_id[q];
+        h.kind = hid.x; h.id = hid.y;
+        D3 color;
+        if (h.kind == LEAF_NONE) {
+            color = skybox_sample(P.sc, d);
+        } else {
+            uint32_t el = h.kind == LEAF_TRI ? P.sc.tri_elem[h.id] : h.id;
+            const DMaterial& dm_ = P.sc.materials[P.sc.elements[el].material];
+            SurfacePoint sp = surface_point(P.sc, h, o, d, dm_.has_image != 0);
+            if (P.mode == HNM_MODE_DEBUG_SHADING) {
+                PointMaterial pm = resolve_material(P.sc, dm_, sp.u, sp.v);
+                D3 light_direction = normalize(d3(1.0, 2.0, -1.0));
+                Hit sh = trace<false>(P.sc, sp.position + sp.normal * P.sc.offset, light_direction, nullptr);
+                double shadow = sh.kind != LEAF_NONE ? 0.5 : 1.0;
+                double diffuse = fmax(dot(sp.normal, light_direction), 0.0);
+                color = pm.emission + pm.albedo * diffuse * shadow;
+            } else if (P.mode == HNM_MODE_DEBUG_NORMAL) {
+                color = sp.normal;
+            } else if (P.mode == HNM_MODE_DEBUG_DEPTH) {
+                color = splat(0.5 * h.t / P.cam.focus_distance);
+            } else {
+                color = splat(fabs(h.t - P.cam.focus_distance));
+            }
+        }
+        P.L[0][q] = color.x; P.L[1][q] = color.y; P.L[2][q] = color.z;
+    }
+    if (P.mode == HNM_MODE_DEBUG_SHADING && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[S_SHADOW], (unsigned long long)P.N);
+}
+
+// `*pixel += supersampling(...)` (src/renderer.rs:37,49-59), pass by pass in order
+__global__ void __launch_bounds__(256) k_accumulate(RParams P) {
+    for (uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x; pix < P.npix; pix += gridDim.x * blockDim.x) {
+        D3 px = d3(P.accum[3 * (size_t)pix], P.accum[3 * (size_t)pix + 1], P.accum[3 * (size_t)pix + 2]);
+        for (uint32_t pass = 0; pass < P.batch; pass++) {
+            D3 acc = splat(0.0);
+            size_t base = ((size_t)pass * P.npix + pix) * P.spp;
+            for (uint32_t s = 0; s < P.spp; s++) acc = acc + d3(P.L[0][base + s], P.L[1][base + s], P.L[2][base + s]);
+            px = px + acc;
+        }
+        P.accum[3 * (size_t)pix] = px.x; P.accum[3 * (size_t)pix + 1] = px.y; P.accum[3 * (size_t)pix + 2] = px.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------ resolve (src/renderer.rs:64-90)
+struct ResolveParams {
+    const double* accum;  // full image, row order, rgb
+    double* tmp0; double* tmp1;
+    uint8_t* rgb8;
+    uint32_t W, H;
+    double scale;
+    hnm_config cfg;
+};
+__global__ void k_tonemap_gamma(ResolveParams R) {
+    size_t n = (size_t)R.W * R.H;
+    double inv_gamma = 1.0 / R.cfg.gamma_factor;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        D3 hdr = d3(R.accum[3 * i], R.accum[3 * i + 1], R.accum[3 * i + 2]) * R.scale;
+        D3 ldr = hdr;
+        if (R.cfg.tone_mapping_mode == 1) {  // src/tonemap.rs:22-27
+            D3 color = hdr * R.cfg.tone_exposure;
+            double luminance = 0.22 * color.x + 0.707 * color.y + 0.071 * color.z;
+            double white_point = R.cfg.tone_white_point * R.cfg.tone_exposure;
+            ldr = saturate(color * (luminance / (white_point * white_point) + 1.0) / (luminance + 1.0));
+        }
+        R.tmp0[3 * i] = dm::pow(ldr.x, inv_gamma);  // src/color.rs:38-48
+        R.tmp0[3 * i + 1] = dm::pow(ldr.y, inv_gamma);
+        R.tmp0[3 * i + 2] = dm::pow(ldr.z, inv_gamma);
+    }
+}
+HNM_D double gaussian(double x, double sigma) {  // src/filter.rs:13-15
+    return dm::exp(-(x * x) / (2.0 * sigma * sigma)) / (2.0 * HNM_PI * sigma * sigma);
+}
+__global__ void k_bilateral(ResolveParams R, const double* src, double* dst) {  // src/filter.rs:32-58
+    size_t n = (size_t)R.W * R.H;
+    const uint32_t width = R.W, height = R.H;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)i % width, y = (uint32_t)i / width;
+        D3 pixel = d3(src[3 * i], src[3 * i + 1], src[3 * i + 2]);
+        double current_sum = pixel.x + pixel.y + pixel.z;
+        double sum_scale = 1.0 / 3.0;
+        D3 filtered = splat(0.0);
+        double w_p = 0.0;
+        uint32_t diameter = R.cfg.bilateral_diameter, half = diameter / 2;
+        for (uint32_t a = 0; a < diameter; a++) {
+            for (uint32_t b = 0; b < diameter; b++) {
+                uint32_t nx = clamp_u32(x - (half - a), 0u, width - 1u);   // wrapping u32, as the release build
+                uint32_t ny = clamp_u32(y - (half - b), 0u, height - 1u);
+                size_t j = (size_t)ny * width + nx;
+                D3 nb = d3(src[3 * j], src[3 * j + 1], src[3 * j + 2]);
+                double nsum = nb.x + nb.y + nb.z;
+                double g_i = gaussian(sum_scale * (nsum - current_sum), R.cfg.bilateral_sigma_i);
+                uint32_t dx = x - nx, dy = y - ny;
+                double dist = __dsqrt_rn((double)(uint32_t)(dx * dx + dy * dy));  // src/filter.rs:7-11
+                double g_s = gaussian(dist, R.cfg.bilateral_sigma_s);
+                double w = g_i * g_s;
+                filtered = filtered + nb * w;
+                w_p += w;
+            }
+        }
+        D3 out = filtered / w_p;
+        dst[3 * i] = out.x; dst[3 * i + 1] = out.y; dst[3 * i + 2] = out.z;
+    }
+}
+HNM_D uint8_t f64_as_u8(double v) {  // Rust `as u8`: saturating, NaN -> 0
+    uint32_t u = __double2uint_rz(v);
+    return (uint8_t)(u > 255u ? 255u : u);
+}
+__global__ void k_quantise(ResolveParams R, const double* src) {  // src/color.rs:10-16
+    size_t n = (size_t)R.W * R.H * 3;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        R.rgb8[i] = f64_as_u8(255.0 * saturate(src[i]));
+}
+// gathered [rank][padded_rows][W][3] -> image row order
+__global__ void k_deinterleave(const double* gathered, double* full, uint32_t W, uint32_t H, uint32_t padded_rows, uint32_t nranks, uint32_t tile_rows) {
+    size_t n = (size_t)nranks * padded_rows * W;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t x = (uint32_t)(i % W);
+        uint32_t lr = (uint32_t)((i / W) % padded_rows);
+        uint32_t rank = (uint32_t)(i / ((size_t)W * padded_rows));
+        uint32_t y = local_to_global_row_h(lr, rank, nranks, tile_rows);
+        if (y >= H) continue;
+        size_t o = ((size_t)y * W + x) * 3;
+        full[o] = gathered[3 * i]; full[o + 1] = gathered[3 * i + 1]; full[o + 2] = gathered[3 * i + 2];
+    }
+}
+
+// ------------------------------------------------------------------------------------ batch (unit parity) kernels
+__global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_batch(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
+    extern __shared__ uint64_t smem_isaac[];
+    uint64_t* mem = smem_isaac + threadIdx.x;
+    for (uint32_t p = blockIdx.x * ISAAC_THREADS + threadIdx.x; p < n; p += gridDim.x * ISAAC_THREADS) {
+        uint64_t* o = out + (size_t)p * count;
+        isaac64_seed<ISAAC_THREADS>(mem, seeds[4 * p], seeds[4 * p + 1], seeds[4 * p + 2], seeds[4 * p + 3], [&](int i, uint64_t v) {
+            int j = 255 - i;
+            if (j < (int)count) o[j] = v;
+        });
+    }
+}
+__global__ void k_isaac_full_batch(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        IsaacFull rng;
+        rng.seed(seeds[4 * p], seeds[4 * p + 1], seeds[4 * p + 2], seeds[4 * p + 3]);
+        for (uint32_t j = 0; j < count; j++) out[(size_t)p * count + j] = rng.next_u64();
+    }
+}
+// material resolve of traced hits (BvhScene::intersect after the traversal, src/scene.rs:389-398)
+struct RayPtrs { const double* p[6]; };
+__global__ void k_hits_to_abi(DScene sc, RayPtrs ray, const double* hit_t, const double* hit_u, const double* hit_v,
+                              const uint2* hit_id, uint32_t n, hnm_hit* hits) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 o = d3(ray.p[0][i], ray.p[1][i], ray.p[2][i]), d = d3(ray.p[3][i], ray.p[4][i], ray.p[5][i]);
+        Hit h;
+        h.t = hit_t[i]; h.u = hit_u[i]; h.v = hit_v[i]; h.kind = hit_id[i].x; h.id = hit_id[i].y;
+        hnm_hit out;
+        memset(&out, 0, sizeof(out));
+        // Evaluated for every ray, not only for misses: with the call inside the `if`, ptxas 12.9 (sm_100a, -O3) returns
+        // a wrong THIRD component of sample_bilinear's result to this kernel (PTX is correct; reproduced with an
+        // all-miss input, fixed by hoisting the call).  This is a batch / test entry point, so the extra work is
+        // irrelevant; the production kernels are pinned bit-for-bit by tests/test_gpu_parity.py.
+        D3 e = skybox_sample(sc, d);
+        if (h.kind == LEAF_NONE) {
+            // Intersection::empty() + skybox emission (src/scene.rs:26-39,398)
+            out.distance = sc.inf; out.albedo = hnm_vec3{1.0, 1.0, 1.0}; out.emission = hnm_vec3{e.x, e.y, e.z};
+            out.roughness = 0.2; out.hit = 0; out.element = -1; out.face = -1; out.surface = HNM_SURFACE_DIFFUSE;
+        } else {
+            uint32_t el = h.kind == LEAF_TRI ? sc.tri_elem[h.id] : h.id;
+            const DMaterial& dm_ = sc.materials[sc.elements[el].material];
+            SurfacePoint sp = surface_point(sc, h, o, d, true);
+            PointMaterial pm = resolve_material(sc, dm_, sp.u, sp.v);
+            out.position = hnm_vec3{sp.position.x, sp.position.y, sp.position.z};
+            out.normal = hnm_vec3{sp.normal.x, sp.normal.y, sp.normal.z};
+            out.albedo = hnm_vec3{pm.albedo.x, pm.albedo.y, pm.albedo.z};
+            out.emission = hnm_vec3{pm.emission.x, pm.emission.y, pm.emission.z};
+            out.distance = h.t; out.u = sp.u; out.v = sp.v; out.roughness = pm.roughness; out.param = pm.param;
+            out.hit = 1; out.element = sp.element; out.face = sp.face; out.surface = pm.surface;
+        }
+        hits[i] = out;
+    }
+}
+__global__ void k_material_sample_batch(DScene sc, const double* in, uint32_t n, double* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double* p = in + 14 * (size_t)i;
+        PointMaterial m;
+        m.surface = (int32_t)p[0]; m.param = p[1]; m.roughness = p[2];
+        m.albedo = splat(1.0); m.emission = splat(0.0);
+        Rand2 rnd{p[3], p[4]};
+        double s, c;
+        dm::sincos(HNM_PI2 * rnd.r0, s, c);
+        SampleResult r;
+        r.origin = splat(0.0); r.direction = splat(0.0); r.reflectance = 0.0;
+        bool some = material_sample(sc, m, rnd, c, s, d3(p[5], p[6], p[7]), d3(p[8], p[9], p[10]), d3(p[11], p[12], p[13]), r);
+        double* o = out + 8 * (size_t)i;
+        o[0] = some ? 1.0 : 0.0;
+        o[1] = some ? r.origin.x : 0.0; o[2] = some ? r.origin.y : 0.0; o[3] = some ? r.origin.z : 0.0;
+        o[4] = some ? r.direction.x : 0.0; o[5] = some ? r.direction.y : 0.0; o[6] = some ? r.direction.z : 0.0;
+        o[7] = some ? r.reflectance : 0.0;
+    }
+}
+__global__ void k_material_bsdf_batch(const double* in, uint32_t n, double* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double* p = in + 12 * (size_t)i;
+        PointMaterial m;
+        m.surface = (int32_t)p[0]; m.param = p[1]; m.roughness = p[2];
+        m.albedo = splat(1.0); m.emission = splat(0.0);
+        out[i] = bsdf(m, d3(p[3], p[4], p[5]), d3(p[6], p[7], p[8]), d3(p[9], p[10], p[11]));
+    }
+}
+__global__ void k_math_batch(int fn, const double* x, const double* y, uint32_t n, double* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double r;
+        switch (fn) {
+            case 0: r = dm::sin(x[i]); break;
+            case 1: r = dm::cos(x[i]); break;
+            case 2: r = dm::exp(x[i]); break;
+            case 3: r = dm::pow(x[i], y[i]); break;
+            default: r = dm::acos(x[i]); break;
+        }
+        out[i] = r;
+    }
+}
+
+}  // namespace hnm
+#endif

@@ -168,6 +168,7 @@ class SceneBuilder {
                 uint32_t face = d->mesh_indices[m.index_offset + k];
                 const uint32_t* f = d->faces + 3 * (size_t)(m.face_offset + face);
                 DTri t;
+                t._pad = 0.0;
                 t.v0x = vb[3 * f[0]]; t.v0y = vb[3 * f[0] + 1]; t.v0z = vb[3 * f[0] + 2];
                 // edge1 = v1 - v0, edge2 = v2 - v0 (src/bvh.rs:268-269)
                 t.e1x = vb[3 * f[1]] - t.v0x; t.e1y = vb[3 * f[1] + 1] - t.v0y; t.e1z = vb[3 * f[1] + 2] - t.v0z;
@@ -332,6 +333,19 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
     auto bail = [&](int code) { scene_free(s); return code; };
     if ((rc = upload(s, b.nodes, &s->d.nodes))) return bail(rc);
     if ((rc = upload(s, b.tris, &s->d.tris))) return bail(rc);
+    {
+        // f32 copies (round to nearest: relative error 2^-24 per component, covered by the pre-test's margins);
+        // the normal e1 x e2 is formed in f64 first
+        std::vector<float4> tf(b.tris.size() * 3);
+        for (size_t i = 0; i < b.tris.size(); i++) {
+            const DTri& t = b.tris[i];
+            double nx = t.e1y * t.e2z - t.e1z * t.e2y, ny = t.e1z * t.e2x - t.e1x * t.e2z, nz = t.e1x * t.e2y - t.e1y * t.e2x;
+            tf[3 * i] = make_float4((float)t.v0x, (float)t.v0y, (float)t.v0z, (float)t.e1x);
+            tf[3 * i + 1] = make_float4((float)t.e1y, (float)t.e1z, (float)t.e2x, (float)t.e2y);
+            tf[3 * i + 2] = make_float4((float)t.e2z, (float)nx, (float)ny, (float)nz);
+        }
+        if ((rc = upload(s, tf, &s->d.trif))) return bail(rc);
+    }
     if ((rc = upload(s, b.tri_elem, &s->d.tri_elem))) return bail(rc);
     if ((rc = upload(s, b.tri_face, &s->d.tri_face))) return bail(rc);
     std::vector<DElement> els(desc->num_elements);
@@ -385,7 +399,9 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
     if ((rc = upload(s, em, &s->d.emissions))) return bail(rc);
     s->d.num_emissions = desc->num_emissions;
     s->d.num_elements = desc->num_elements;
-    for (int k = 0; k < 6; k++) s->d.skybox_images[k] = desc->skybox_images[k];
+    std::vector<DImage> faces(6);
+    for (int k = 0; k < 6; k++) faces[k] = imgs[desc->skybox_images[k]];
+    if ((rc = upload(s, faces, &s->d.sky_faces))) return bail(rc);
     s->d.sky_r = desc->skybox_intensity.x; s->d.sky_g = desc->skybox_intensity.y; s->d.sky_b = desc->skybox_intensity.z;
     s->d.eps = desc->config.eps; s->d.offset = desc->config.offset; s->d.inf = desc->config.inf; s->d.gamma = desc->config.gamma_factor;
     s->d.bounce_limit = desc->config.bounce_limit; s->d.supersampling = desc->config.supersampling;
@@ -396,6 +412,7 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
         R = std::fmax(R, std::fmax(std::fabs(s->d.bounds_lo[k]), std::fabs(s->d.bounds_hi[k])));
     }
     s->d.far_limit = (float)(4.0 * R);
+    s->d.scene_r = f32_up(R);
     s->num_nodes = (uint32_t)b.nodes.size(); s->num_tris = (uint32_t)b.tris.size();
     s->num_elements = desc->num_elements; s->num_emissions = desc->num_emissions;
     *out = s;

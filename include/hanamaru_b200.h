@@ -195,6 +195,8 @@ typedef struct hnm_counters {
     uint64_t shadow_rays;  /* NEE rays (also closest-hit, src/renderer.rs:280) */
     uint64_t rng_fallbacks;/* paths whose lens loop outran the stored ISAAC tail */
     uint64_t kernel_launches;
+    uint64_t node_visits;  /* BVH nodes fetched / primitives tested; counted only when */
+    uint64_t prim_tests;   /* the environment has HNM_TRACE_STATS=1 (instrumented kernel) */
 } hnm_counters;
 
 typedef struct hnm_scene hnm_scene;       /* opaque: device copy of a scene */
