@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A)
     float l0 = 0.f, l1_ = 0.f, l2 = 0.f, l3 = 0.f;
     int ncand = 0;
     uint32_t n_nodes = 0, n_prims = 0;
+    bool more = true;  // warp-uniform: the work counter has not run past the end yet
+    uint32_t lk = 0;   // next primitive of the leaf this lane holds
 
 #define HNM_EXACT(g)                                               \
     {                                                              \
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A)
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(A.work, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                more = base + (uint32_t)__popc(need) < ntot;
                 if (!has_ray) {
                     idx = base + __popc(need & ((1u << lane) - 1u));
                     if (idx < ntot) {
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A)
                         has_ray = true;
                         sp = 0;
                         cur = 0;
+                        lk = 0;
                         float fmaxo = fmaxf(fmaxf(fabsf((float)o.x), fabsf((float)o.y)), fabsf((float)o.z));
                         if (fmaxo > sc.far_limit) {
                             double dist;
@@ -216,63 +220,76 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A)
             if (__ballot_sync(0xFFFFFFFFu, has_ray || pending) == 0) break;
         }
         // ---- traverse (f32) until too few lanes are left -----------------------------------------------------
-        bool go = has_ray;
-        while (go) {
+        // Majority-vote scheduling.  Each iteration every lane is in one of two states: it holds a NODE (cur >= 0)
+        // or a LEAF with triangles left (cur < 0).  The warp executes ONE step of whichever kind the majority of
+        // lanes needs -- a node step (two f32 slab tests) or a leaf step (one f32 triangle pre-test) -- and the
+        // minority idles until it becomes the majority.  The loop is warp-uniform (full-mask ballots): with
+        // independent thread scheduling a per-lane `while (has_ray)` never reconverges, and a strict while-while
+        // loop (all lanes descend to a leaf, then all test it) ran at 4 of 32 lanes per instruction on the
+        // incoherent bounces because the longest descent of the warp sets the pace (ncu, round 1).
+        unsigned act = __ballot_sync(0xFFFFFFFFu, has_ray);
+        while (act) {
             bool done = false;
-            // node phase
-            while (cur >= 0) {
-                const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-                float4 m0 = __ldg(np), m1 = __ldg(np + 1), m2 = __ldg(np + 2);
-                int4 m3 = __ldg(reinterpret_cast<const int4*>(np + 3));
-                if (STATS) n_nodes++;
-                float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
-                float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
-                float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
-                float tmin0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
-                float tmax0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
-                float g0 = (m1.z - R.ox) * R.ix, e0 = (m2.y - R.ox) * R.ix;
-                float g1 = (m1.w - R.oy) * R.iy, e1 = (m2.z - R.oy) * R.iy;
-                float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
-                float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
-                float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
-                float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
-                float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
-                bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= best_ub);
-                bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= best_ub);
-                if (h0 && h1) {
-                    bool swap = lo1 < lo0;
-                    if (sp < HNM_STACK) stack[sp++] = swap ? m3.x : m3.y;
-                    cur = swap ? m3.y : m3.x;
-                } else if (h0) {
-                    cur = m3.x;
-                } else if (h1) {
-                    cur = m3.y;
-                } else {
-                    if (sp == 0) { done = true; break; }
-                    cur = stack[--sp];
-                }
-            }
-            if (!done) {
-                int kind = leaf_kind(cur);
-                uint32_t first = leaf_first(cur);
-                if (kind == LEAF_TRI) {
-                    uint32_t cnt = leaf_count(cur);
-                    for (uint32_t k = 0; k < cnt; k++) {
-                        float tlo;
-                        if (tri_pretest(sc.trif + 3 * (size_t)(first + k), R, best_ub, &tlo)) {
-                            if (ncand == 4) {
-                                // list full: the oldest entry either drops out (bound moved below it) or is confirmed now
-                                if (l3 <= best_ub) {
-                                    HNM_EXACT(c3)
-                                    best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
-                                }
-                                ncand = 3;
-                            }
-                            c3 = c2; l3 = l2; c2 = c1; l2 = l1_; c1 = c0; l1_ = l0;
-                            c0 = first + k; l0 = tlo;
-                            ncand++;
-                        }
+            const bool is_node = has_ray && cur >= 0;
+            const unsigned nm = __ballot_sync(0xFFFFFFFFu, is_node);
+            if (2 * __popc(nm) >= __popc(act)) {
+                if (is_node) {
+                    const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+                    float4 m0 = __ldg(np), m1 = __ldg(np + 1), m2 = __ldg(np + 2);
+                    int4 m3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+                    if (STATS) n_nodes++;
+                    float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
+                    float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
+                    float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
+                    float tmin0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+                    float tmax0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+                    float g0 = (m1.z - R.ox) * R.ix, e0 = (m2.y - R.ox) * R.ix;
+                    float g1 = (m1.w - R.oy) * R.iy, e1 = (m2.z - R.oy) * R.iy;
+                    float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
+                    float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
+                    float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
+                    float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
+                    float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
+                    bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= best_ub);
+                    bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= best_ub);
+                    if (h0 && h1) {
+                        bool swap = lo1 < lo0;
+                        if (sp < HNM_STACK) stack[sp++] = swap ? m3.x : m3.y;
+                        cur = swap ? m3.y : m3.x;
+                    } else if (h0) {
+                        cur = m3.x;
+                    } else if (h1) {
+                        cur = m3.y;
+                    } else if (sp == 0) {
+                        done = true;
+                    } else {
+                        cur = stack[--sp];
                     }
+                    lk = 0;
+                }
+            } else if (has_ray && !is_node) {
+                // one primitive of the leaf this lane holds
+                const int kind = leaf_kind(cur);
+                const uint32_t first = leaf_first(cur);
+                bool leaf_done = true;
+                if (kind == LEAF_TRI) {
+                    float tlo;
+                    const uint32_t g = first + lk;
+                    if (tri_pretest(sc.trif + 3 * (size_t)g, R, best_ub, &tlo)) {
+                        if (ncand == 4) {
+                            // list full: the oldest entry either drops out (bound moved below it) or is confirmed now
+                            if (l3 <= best_ub) {
+                                HNM_EXACT(c3)
+                                best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
+                            }
+                            ncand = 3;
+                        }
+                        c3 = c2; l3 = l2; c2 = c1; l2 = l1_; c1 = c0; l1_ = l0;
+                        c0 = g; l0 = tlo;
+                        ncand++;
+                    }
+                    lk++;
+                    leaf_done = lk >= leaf_count(cur);
                 } else if (kind == LEAF_SPHERE) {
                     if (STATS) n_prims++;
                     sphere_test(sc.elements[first], first, sc.elements, o, dir, best);
@@ -282,18 +299,19 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A)
                     cuboid_test(sc.elements[first], first, sc.elements, o, dir, best);
                     best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
                 }
-                if (sp == 0) done = true;
-                else cur = stack[--sp];
+                if (leaf_done) {
+                    lk = 0;
+                    if (sp == 0) done = true;
+                    else cur = stack[--sp];
+                }
             }
             if (done) {
                 has_ray = false;
                 pending = true;
-                go = false;
-            } else if (__popc(__activemask()) < TRACE_REFILL) {
-                go = false;  // too few lanes left: let the warp refill (this lane keeps its state)
             }
+            act = __ballot_sync(0xFFFFFFFFu, has_ray);
+            if (more && __popc(act) < TRACE_REFILL) break;  // too few lanes left: refill (lanes keep their state)
         }
-        __syncwarp();
     }
 #undef HNM_EXACT
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.stat_segments >= 0) atomicAdd(&A.stats[A.stat_segments], (unsigned long long)n0);
