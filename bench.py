@@ -246,13 +246,15 @@ def run_ours(args):
         paths_p = pc["paths"]
         seg, sh = pc["segments"], pc["shadow_rays"]
         nee_events = sh / max(1, scene.desc.contents.num_emissions)
-        # algorithmic bytes (f64 records actually shipped; DESIGN.md section "records"):
-        #   extend   : read ray 48 + pid 4, write hit 32, write one queue entry 4            = 88 B / segment
-        #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17, L rmw 48,
-        #              write next ray 76 (only surviving paths; counted for all)                = 253 B / NEE event
-        #   isaac    : write 32-word tail 256 + ray 76 + L 24 + cursor 1                       = 357 B / path
-        per_unit = {"extend": (88.0, seg), "shade_nee": (253.0, nee_events), "isaac_raygen": (357.0, paths_p),
-                    "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p), "shade_delta": (253.0 - 48.0, seg - nee_events)}
+        # algorithmic bytes per unit (the f64 SoA records actually shipped; DESIGN.md "HBM records"):
+        #   trace    : per ray: read origin+direction 48, write hit (t,u,v 24 + kind/id 8) 32; camera rays also
+        #              write one 4-byte queue entry                                    = 84 B / segment, 80 B / shadow ray
+        #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17; write next ray 76 (survivors; counted
+        #              for all) + event 76 + shadow ray 88                              = 369 B / NEE event
+        #   isaac    : write 32-word tail 256 + ray 76 + L 24 + cursor 1               = 357 B / path
+        per_unit = {"trace": ((84.0 * seg + 80.0 * sh) / max(1, seg + sh), seg + sh), "shade_nee": (369.0, nee_events),
+                    "isaac_raygen": (357.0, paths_p), "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p),
+                    "shade_delta": (4 + 48 + 24 + 4 + 32 + 17 + 48 + 76.0, seg - nee_events)}
         if top in per_unit:
             b, units = per_unit[top]
             ms, nl = ktimes[top]

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-CORE_LIB = os.path.join(HERE, "libhanamaru_b200.so")
+CORE_LIB = os.environ.get("HNM_CORE_LIB") or os.path.join(HERE, "libhanamaru_b200.so")  # override: tuning experiments only
 HOST_LIB = os.path.join(HERE, "libhanamaru_host.so")
 
 HNM_ABI_VERSION = 1

@@ -60,7 +60,7 @@ struct hnm_renderer {
     double* thr_buf[2][3] = {};
     uint32_t* pid_buf[2] = {};
     int sm_count = 148;
-    int trace_blocks_per_sm = 4;
+    int trace_blocks_per_sm = HNM_TRACE_MIN_BLOCKS;  // persistent CTAs per SM = what the register budget allows
     cudaEvent_t marks[16] = {};
 };
 

@@ -25,8 +25,14 @@
 
 namespace hnm {
 
+#ifndef HNM_TRACE_MIN_BLOCKS
+#define HNM_TRACE_MIN_BLOCKS 5  /* 96 registers: measured best of 4 (108 regs) / 5 / 6 (80 regs, spills) */
+#endif
+#ifndef HNM_TRACE_REFILL
+#define HNM_TRACE_REFILL 20
+#endif
 constexpr int TRACE_THREADS = 128;
-constexpr int TRACE_REFILL = 20;  // refetch when fewer lanes than this are still traversing
+constexpr int TRACE_REFILL = HNM_TRACE_REFILL;  // refetch when fewer lanes than this are still traversing
 
 struct TraceJob {
     const double* ray[6];  // origin xyz, direction xyz (SoA)
@@ -106,7 +112,7 @@ HNM_D bool tri_pretest(const float4* __restrict__ tf, const RayF& R, float& best
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(DScene sc, TraceArgs A) {
+__global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(DScene sc, TraceArgs A) {
     const int lane = threadIdx.x & 31;
     const uint32_t n0 = *A.job[0].count;
     const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
