@@ -53,7 +53,7 @@ struct hnm_renderer {
     size_t cap = 0;
     double *tmp0 = nullptr, *tmp1 = nullptr;
     uint8_t* rgb8 = nullptr;
-    bool profiling = false, trace_stats = false;
+    bool profiling = false, trace_stats = false, per_bounce_names = false;
     uint64_t launches = 0;
     KernelTimer timer;
     double* ray_buf[2][6] = {};
@@ -117,6 +117,13 @@ TraceJob shadow_job(const RParams& P, int bounce) {
     return j;
 }
 
+// diagnostics: HNM_TRACE_NAMES=1 times every bounce's trace launch under its own name
+const char* trace_name(hnm_renderer* r, int bounce) {
+    static const char* names[] = {"trace_b00", "trace_b01", "trace_b02", "trace_b03", "trace_b04", "trace_b05", "trace_b06", "trace_b07",
+                                  "trace_b08", "trace_b09", "trace_b10", "trace_b11", "trace_b12"};
+    return (r->per_bounce_names && bounce >= 0 && bounce <= 12) ? names[bounce] : "trace";
+}
+
 void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const TraceJob* j1, uint32_t* work, int stat_segments) {
     TraceArgs A;
     memset(&A, 0, sizeof(A));
@@ -155,10 +162,10 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch) {
             TraceJob cam = camera_job(P, b, true);
             if (b > 1) {
                 TraceJob sh = shadow_job(P, b - 1);
-                launch_trace(r, "trace", &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
+                launch_trace(r, trace_name(r, b), &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
                 launch_timed(r, "nee_resolve", [&] { k_nee_resolve<<<grid, 256, 0, st>>>(P, b - 1); });
             } else {
-                launch_trace(r, "trace", &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
+                launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
             }
             launch_timed(r, "shade_miss", [&] { k_shade_miss<<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_delta", [&] { k_shade_surf<false><<<grid, 256, 0, st>>>(P, b); });
@@ -166,7 +173,7 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch) {
             buf ^= 1;
         }
         TraceJob sh = shadow_job(P, last);
-        launch_trace(r, "trace", &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1);
+        launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1);
         launch_timed(r, "nee_resolve", [&] { k_nee_resolve<<<grid, 256, 0, st>>>(P, last); });
     } else {
         select_buffers(r, 1);
@@ -232,6 +239,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     P.tail_k = RNG_TAIL;
     if (const char* e = getenv("HNM_RNG_TAIL_K")) { int k = atoi(e); if (k >= 2 && k <= RNG_TAIL) P.tail_k = k & ~1; }
     if (const char* e = getenv("HNM_TRACE_STATS")) r->trace_stats = atoi(e) != 0;
+    if (const char* e = getenv("HNM_TRACE_NAMES")) r->per_bounce_names = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     uint32_t ntiles = (height + sh.tile_rows - 1) / sh.tile_rows;
     uint32_t tiles_per_rank = (ntiles + sh.num_ranks - 1) / sh.num_ranks;

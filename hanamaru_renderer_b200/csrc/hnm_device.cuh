@@ -121,7 +121,9 @@ HNM_D DTri load_tri(const DTri* p) {
 struct DScene {
     const DNode* nodes;
     const DTri* tris;
-    const float4* trif;        // f32 copy for the conservative pre-test: 3 x float4 per triangle = v0, e1, e2, e1 x e2
+    const float4* trif;        // f32 copy for the conservative pre-test: 3 x float4 per triangle = v0, e1, e2, e1 x e2,
+                               // in TRAVERSAL order (the leaves of the GPU-side tree index this array)
+    const uint32_t* tri_perm;  // traversal position -> index into tris[] (the reference's leaf order)
     float scene_r;             // max |coordinate| of the scene box (error bound of the f32 origin)
     const uint32_t* tri_elem;  // element id per triangle
     const uint32_t* tri_face;  // face index inside its mesh
@@ -280,9 +282,10 @@ HNM_D Hit trace(const DScene& sc, D3 o, D3 dir, TraceStats* st) {
             if (kind == LEAF_TRI) {
                 uint32_t cnt = leaf_count(cur);
                 for (uint32_t k = 0; k < cnt; k++) {
-                    DTri tr = load_tri(sc.tris + (first + k));
+                    uint32_t g = __ldg(sc.tri_perm + first + k);
+                    DTri tr = load_tri(sc.tris + g);
                     if (STATS) st->prims++;
-                    tri_test(tr, first + k, o, dir, best);
+                    tri_test(tr, g, o, dir, best);
                 }
             } else if (kind == LEAF_SPHERE) {
                 if (STATS) st->prims++;

@@ -184,11 +184,17 @@ class SceneBuilder {
         if (!bounds.empty)
             for (int k = 0; k < 3; k++) R = std::fmax(R, std::fmax(std::fabs(bounds.lo[k]), std::fabs(bounds.hi[k])));
         pad = std::fmax(R, 1e-30) * 0x1p-19;  // absolute slack for the f32 rounding of (box - origin)
-        // 2. one tree: node 0 is reserved for the root
+        // 2. one tree: node 0 is reserved for the root.  Default: a fresh SAH tree over ALL primitives (results do not
+        //    depend on the tree -- DESIGN.md section 2 -- only the number of visits does; the host's median-split
+        //    trees cost ~1.5x more node visits).  HNM_BVH=ref keeps the host's topology (A/B and debugging).
         nodes.clear();
         nodes.push_back(DNode{});
         BoxD rb;
-        int32_t root = build_top(0, rb);
+        const char* mode = getenv("HNM_BVH");
+        const bool use_ref = mode && std::string(mode) == "ref";
+        tri_order.resize(tris.size());
+        for (size_t i = 0; i < tris.size(); i++) tri_order[i] = (uint32_t)i;
+        int32_t root = use_ref ? build_top(0, rb) : build_sah(rb);
         if (root >= 0) {
             nodes[0] = nodes[root];
         } else {
@@ -201,9 +207,134 @@ class SceneBuilder {
         return true;
     }
 
+    std::vector<uint32_t> tri_order;  // traversal (leaf) position -> triangle index in the reference's leaf order
+
   private:
     const hnm_scene_desc* d_;
     std::vector<uint32_t> mesh_tri_base_;
+
+    // ---- binned SAH build over every primitive of the scene (triangles, spheres, cuboids) ------------------
+    struct Prim {
+        BoxD box;
+        double c[3];
+        int kind;      // LEAF_TRI / LEAF_SPHERE / LEAF_CUBOID
+        uint32_t id;   // triangle index (reference leaf order) or element id
+    };
+    static double half_area(const BoxD& b) {
+        if (b.empty) return 0.0;
+        double dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+    int32_t sah_rec(std::vector<Prim>& prims, size_t lo, size_t hi, std::vector<uint32_t>& order, BoxD& out) {
+        out = BoxD();
+        BoxD cb;  // centroid bounds
+        bool all_tri = true;
+        for (size_t i = lo; i < hi; i++) {
+            out.grow(prims[i].box);
+            BoxD c;
+            c.empty = false;
+            for (int k = 0; k < 3; k++) c.lo[k] = c.hi[k] = prims[i].c[k];
+            cb.grow(c);
+            all_tri = all_tri && prims[i].kind == LEAF_TRI;
+        }
+        const size_t n = hi - lo;
+        auto make_leaf = [&]() -> int32_t {
+            if (prims[lo].kind != LEAF_TRI) return leaf_link(prims[lo].kind, 1, prims[lo].id);
+            uint32_t first = (uint32_t)order.size();
+            for (size_t i = lo; i < hi; i++) order.push_back(prims[i].id);
+            return leaf_link(LEAF_TRI, (uint32_t)n, first);
+        };
+        if (n == 1) return make_leaf();
+        // best binned split over the three axes
+        const int NB = 32;
+        double best_cost = 1e300;
+        int best_axis = -1, best_bin = -1;
+        const double parent_area = std::fmax(half_area(out), 1e-300);
+        for (int axis = 0; axis < 3; axis++) {
+            double ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0.0)) continue;
+            BoxD bb[NB];
+            size_t cnt[NB] = {0};
+            for (size_t i = lo; i < hi; i++) {
+                int b = (int)((prims[i].c[axis] - cb.lo[axis]) / ext * NB);
+                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                bb[b].grow(prims[i].box);
+                cnt[b]++;
+            }
+            double right_area[NB];
+            size_t right_cnt[NB];
+            BoxD acc;
+            size_t c = 0;
+            for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); c += cnt[b]; right_area[b] = half_area(acc); right_cnt[b] = c; }
+            acc = BoxD();
+            c = 0;
+            for (int b = 0; b < NB - 1; b++) {
+                acc.grow(bb[b]);
+                c += cnt[b];
+                if (c == 0 || right_cnt[b + 1] == 0) continue;
+                double cost = 1.0 + (half_area(acc) * (double)c + right_area[b + 1] * (double)right_cnt[b + 1]) / parent_area;
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        const double leaf_cost = (double)n;  // one pre-test per triangle ~ one node step
+        if (all_tri && n <= 7 && (best_axis < 0 || leaf_cost <= best_cost)) return make_leaf();
+        size_t mid;
+        if (best_axis >= 0) {
+            double ext = cb.hi[best_axis] - cb.lo[best_axis], base = cb.lo[best_axis];
+            auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const Prim& p) {
+                int b = (int)((p.c[best_axis] - base) / ext * NB);
+                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
+                return b <= best_bin;
+            });
+            mid = (size_t)(it - prims.begin());
+        } else {
+            mid = lo + n / 2;  // identical centroids: split by count
+        }
+        if (mid == lo || mid == hi) mid = lo + n / 2;
+        int32_t slot = (int32_t)nodes.size();
+        nodes.push_back(DNode{});
+        BoxD b0, b1;
+        int32_t l0 = sah_rec(prims, lo, mid, order, b0);
+        int32_t l1 = sah_rec(prims, mid, hi, order, b1);
+        return make_inner(l0, b0, l1, b1, slot);
+    }
+    int32_t build_sah(BoxD& out) {
+        std::vector<Prim> prims;
+        prims.reserve(tris.size() + d_->num_elements);
+        for (size_t g = 0; g < tris.size(); g++) {
+            const DTri& t = tris[g];
+            // the vertices as the host stored them: v1 = v0 + e1 is not bit-exact, so box the three points generously
+            double vx[3] = {t.v0x, t.v0x + t.e1x, t.v0x + t.e2x}, vy[3] = {t.v0y, t.v0y + t.e1y, t.v0y + t.e2y}, vz[3] = {t.v0z, t.v0z + t.e1z, t.v0z + t.e2z};
+            Prim p;
+            p.box.empty = false;
+            p.box.lo[0] = std::fmin(vx[0], std::fmin(vx[1], vx[2])); p.box.hi[0] = std::fmax(vx[0], std::fmax(vx[1], vx[2]));
+            p.box.lo[1] = std::fmin(vy[0], std::fmin(vy[1], vy[2])); p.box.hi[1] = std::fmax(vy[0], std::fmax(vy[1], vy[2]));
+            p.box.lo[2] = std::fmin(vz[0], std::fmin(vz[1], vz[2])); p.box.hi[2] = std::fmax(vz[0], std::fmax(vz[1], vz[2]));
+            for (int k = 0; k < 3; k++) {
+                // v0 + e can differ from the stored vertex by one rounding: widen by 2 ulp of the magnitude
+                double m = std::fmax(std::fabs(p.box.lo[k]), std::fabs(p.box.hi[k])) * 0x1p-51;
+                p.box.lo[k] -= m; p.box.hi[k] += m;
+                p.c[k] = 0.5 * (p.box.lo[k] + p.box.hi[k]);
+            }
+            p.kind = LEAF_TRI;
+            p.id = (uint32_t)g;
+            prims.push_back(p);
+        }
+        for (uint32_t el = 0; el < d_->num_elements; el++) {
+            const hnm_element& e = d_->elements[el];
+            if (e.kind == HNM_ELEM_MESH) continue;
+            Prim p;
+            p.box = element_box(e);
+            if (p.box.empty) continue;
+            for (int k = 0; k < 3; k++) p.c[k] = 0.5 * (p.box.lo[k] + p.box.hi[k]);
+            p.kind = e.kind == HNM_ELEM_SPHERE ? LEAF_SPHERE : LEAF_CUBOID;
+            p.id = el;
+            prims.push_back(p);
+        }
+        tri_order.clear();
+        if (prims.empty()) { out = BoxD(); return leaf_link(LEAF_NONE, 0, 0); }
+        return sah_rec(prims, 0, prims.size(), tri_order, out);
+    }
 
     static int32_t leaf_link(int kind, uint32_t count, uint32_t first) { return ~(int32_t)(((uint32_t)kind << 29) | (count << 26) | first); }
 
@@ -336,15 +467,17 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
     {
         // f32 copies (round to nearest: relative error 2^-24 per component, covered by the pre-test's margins);
         // the normal e1 x e2 is formed in f64 first
-        std::vector<float4> tf(b.tris.size() * 3);
-        for (size_t i = 0; i < b.tris.size(); i++) {
-            const DTri& t = b.tris[i];
+        // ... in TRAVERSAL order (tri_order); candidates map back to the reference order through tri_perm
+        std::vector<float4> tf(b.tri_order.size() * 3);
+        for (size_t i = 0; i < b.tri_order.size(); i++) {
+            const DTri& t = b.tris[b.tri_order[i]];
             double nx = t.e1y * t.e2z - t.e1z * t.e2y, ny = t.e1z * t.e2x - t.e1x * t.e2z, nz = t.e1x * t.e2y - t.e1y * t.e2x;
             tf[3 * i] = make_float4((float)t.v0x, (float)t.v0y, (float)t.v0z, (float)t.e1x);
             tf[3 * i + 1] = make_float4((float)t.e1y, (float)t.e1z, (float)t.e2x, (float)t.e2y);
             tf[3 * i + 2] = make_float4((float)t.e2z, (float)nx, (float)ny, (float)nz);
         }
         if ((rc = upload(s, tf, &s->d.trif))) return bail(rc);
+        if ((rc = upload(s, b.tri_order, &s->d.tri_perm))) return bail(rc);
     }
     if ((rc = upload(s, b.tri_elem, &s->d.tri_elem))) return bail(rc);
     if ((rc = upload(s, b.tri_face, &s->d.tri_face))) return bail(rc);

@@ -280,8 +280,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                 bool leaf_done = true;
                 if (kind == LEAF_TRI) {
                     float tlo;
-                    const uint32_t g = first + lk;
-                    if (tri_pretest(sc.trif + 3 * (size_t)g, R, best_ub, &tlo)) {
+                    const uint32_t pos = first + lk;
+                    if (tri_pretest(sc.trif + 3 * (size_t)pos, R, best_ub, &tlo)) {
+                        const uint32_t g = __ldg(sc.tri_perm + pos);  // index in the reference's leaf order (ties)
                         if (ncand == 4) {
                             // list full: the oldest entry either drops out (bound moved below it) or is confirmed now
                             if (l3 <= best_ub) {
