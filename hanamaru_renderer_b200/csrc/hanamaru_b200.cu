@@ -59,6 +59,24 @@ struct hnm_renderer {
     double* ray_buf[2][6] = {};
     double* thr_buf[2][3] = {};
     uint32_t* pid_buf[2] = {};
+    // Generation sets: everything k_isaac_raygen / k_rng_overflow produce for one batch (first-bounce rays, zeroed
+    // radiance, RNG tail + cursor).  Two sets, so that the set of batch i+1 is filled on `rng_stream` while batch i
+    // is traced and shaded on `stream`: ISAAC seeding is shared-memory-latency bound at 3.5 warps/SM and uses no
+    // registers to speak of, the trace / shade kernels use no shared memory -- they co-reside on every SM.
+    struct GenSet {
+        double* ray[6] = {}; double* thr[3] = {}; uint32_t* pid = nullptr;
+        double* L[3] = {}; uint8_t* cursor = nullptr; uint64_t* tail = nullptr;
+        uint32_t* q_ovf = nullptr; uint32_t* ovf_counter = nullptr;
+        cudaEvent_t ready = nullptr, released = nullptr;
+        bool valid = false;        // holds the generated batch (sampling_first, batch), not consumed yet
+        bool ready_recorded = false, released_recorded = false;
+        uint32_t sampling_first = 0, batch = 0;
+    } gen[2];
+    int num_gen = 1;
+    cudaStream_t rng_stream = nullptr;
+    bool overlap = true;           // HNM_RNG_OVERLAP=0: generate on `stream`, in order (A/B and debugging)
+    bool speculate = true;         // HNM_RNG_SPECULATE=0: no prefetch across hnm_render_passes calls
+    uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
     int trace_blocks_per_sm = HNM_TRACE_MIN_BLOCKS;  // persistent CTAs per SM = what the register budget allows
     cudaEvent_t marks[16] = {};
@@ -67,13 +85,14 @@ struct hnm_renderer {
 namespace {
 
 template <typename F>
-void launch_timed(hnm_renderer* r, const char* name, F&& f) {
+void launch_timed(hnm_renderer* r, const char* name, F&& f, cudaStream_t on = nullptr) {
     r->launches++;
     if (!r->profiling) { f(); return; }
+    if (!on) on = r->stream;
     cudaEvent_t a = r->timer.get(), b = r->timer.get();
-    cudaEventRecord(a, r->stream);
+    cudaEventRecord(a, on);
     f();
-    cudaEventRecord(b, r->stream);
+    cudaEventRecord(b, on);
     r->timer.pending.push_back({name, a, b});
 }
 
@@ -93,6 +112,38 @@ void select_buffers(hnm_renderer* r, int in) {
     for (int k = 0; k < 6; k++) { P.rin[k] = r->ray_buf[in][k]; P.rout[k] = r->ray_buf[in ^ 1][k]; }
     for (int k = 0; k < 3; k++) { P.tin[k] = r->thr_buf[in][k]; P.tout[k] = r->thr_buf[in ^ 1][k]; }
     P.pin = r->pid_buf[in]; P.pout = r->pid_buf[in ^ 1];
+}
+// first bounce: read the generated rays of set `g`, write ray queue 0
+void select_first_bounce(hnm_renderer* r, const hnm_renderer::GenSet& g) {
+    RParams& P = r->P;
+    for (int k = 0; k < 6; k++) { P.rin[k] = g.ray[k]; P.rout[k] = r->ray_buf[0][k]; }
+    for (int k = 0; k < 3; k++) { P.tin[k] = g.thr[k]; P.tout[k] = r->thr_buf[0][k]; }
+    P.pin = g.pid; P.pout = r->pid_buf[0];
+}
+// the per-path state of the batch lives in its generation set
+void bind_gen_set(RParams& P, const hnm_renderer::GenSet& g) {
+    for (int k = 0; k < 3; k++) P.L[k] = g.L[k];
+    P.cursor = g.cursor; P.tail = g.tail; P.q_ovf = g.q_ovf; P.ovf_counter = g.ovf_counter;
+}
+
+// ISAAC seeding + lens sampling + first-bounce rays of batch (sampling_first, batch) into set `g`, on stream `on`
+int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, uint32_t batch, cudaStream_t on) {
+    RParams G = r->P;
+    G.batch = batch;
+    G.sampling_first = sampling_first;
+    G.N = batch * G.npix * G.spp;
+    bind_gen_set(G, g);
+    for (int k = 0; k < 6; k++) G.rout[k] = g.ray[k];
+    for (int k = 0; k < 3; k++) G.tout[k] = g.thr[k];
+    G.pout = g.pid;
+    HNM_CUDA(cudaMemsetAsync(g.ovf_counter, 0, sizeof(uint32_t), on));
+    size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
+    launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<r->sm_count, ISAAC_THREADS, smem, on>>>(G); }, on);
+    launch_timed(r, "rng_overflow", [&] { k_rng_overflow<<<r->sm_count, 64, 0, on>>>(G); }, on);
+    g.valid = true;
+    g.sampling_first = sampling_first;
+    g.batch = batch;
+    return 0;
 }
 
 TraceJob camera_job(const RParams& P, int bounce, bool classify) {
@@ -141,7 +192,9 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     else launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
 }
 
-int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch) {
+// One batch of passes.  (next_first, next_batch) is the batch the caller expects to run after this one (0 = none):
+// its generation is enqueued on the RNG stream BEFORE this batch's kernels, so the two overlap on the device.
+int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t next_first, uint32_t next_batch) {
     RParams& P = r->P;
     P.batch = batch;
     P.sampling_first = sampling_first;
@@ -152,13 +205,42 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch) {
     const int grid = r->sm_count * 4;
     const int last = (int)P.sc.bounce_limit - 1;
     if (P.mode == HNM_MODE_PATHTRACING) {
-        size_t smem = (size_t)ISAAC_THREADS * 256 * sizeof(uint64_t);
-        select_buffers(r, 1);  // ray generation WRITES queue 0
-        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<r->sm_count, ISAAC_THREADS, smem, st>>>(P); });
-        launch_timed(r, "rng_overflow", [&] { k_rng_overflow<<<r->sm_count, 64, 0, st>>>(P); });
-        int buf = 0;
+        const bool overlap = r->overlap && !r->profiling && r->num_gen == 2;
+        // ---- the generation set of this batch: prefetched, or generated now
+        int s = -1;
+        for (int k = 0; k < r->num_gen; k++)
+            if (r->gen[k].valid && r->gen[k].sampling_first == sampling_first && r->gen[k].batch == batch) s = k;
+        if (s < 0) {
+            s = 0;
+            for (int k = 0; k < r->num_gen; k++) if (!r->gen[k].valid) s = k;
+            hnm_renderer::GenSet& g = r->gen[s];
+            if (g.valid) r->gen_wasted++;
+            // the set's last consumer ran on `st`, its last producer possibly on the RNG stream
+            if (g.ready_recorded) HNM_CUDA(cudaStreamWaitEvent(st, g.ready, 0));
+            int rc = generate(r, g, sampling_first, batch, st);
+            if (rc) return rc;
+        } else if (r->gen[s].ready_recorded) {
+            HNM_CUDA(cudaStreamWaitEvent(st, r->gen[s].ready, 0));
+        }
+        hnm_renderer::GenSet& g = r->gen[s];
+        g.valid = false;  // consumed by this batch
+        // ---- prefetch the next batch into the other set (waits until that set's last consumer is done)
+        if (overlap && next_batch > 0) {
+            hnm_renderer::GenSet& o = r->gen[s ^ 1];
+            if (!(o.valid && o.sampling_first == next_first && o.batch == next_batch)) {
+                if (o.valid) r->gen_wasted++;
+                if (o.released_recorded) HNM_CUDA(cudaStreamWaitEvent(r->rng_stream, o.released, 0));
+                int rc = generate(r, o, next_first, next_batch, r->rng_stream);
+                if (rc) return rc;
+                HNM_CUDA(cudaEventRecord(o.ready, r->rng_stream));
+                o.ready_recorded = true;
+            }
+        }
+        bind_gen_set(P, g);
+        launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
         for (int b = 1; b <= last; b++) {
-            select_buffers(r, buf);
+            if (b == 1) select_first_bounce(r, g);
+            else select_buffers(r, b & 1);  // bounce 2 reads queue 0 (written by bounce 1), bounce 3 queue 1, ...
             TraceJob cam = camera_job(P, b, true);
             if (b > 1) {
                 TraceJob sh = shadow_job(P, b - 1);
@@ -170,20 +252,23 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch) {
             launch_timed(r, "shade_miss", [&] { k_shade_miss<<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_delta", [&] { k_shade_surf<false><<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_nee", [&] { k_shade_surf<true><<<grid, 256, 0, st>>>(P, b); });
-            buf ^= 1;
         }
         TraceJob sh = shadow_job(P, last);
         launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1);
         launch_timed(r, "nee_resolve", [&] { k_nee_resolve<<<grid, 256, 0, st>>>(P, last); });
+        launch_timed(r, "accumulate", [&] { k_accumulate<<<grid, 256, 0, st>>>(P); });
+        HNM_CUDA(cudaEventRecord(g.released, st));
+        g.released_recorded = true;
     } else {
+        bind_gen_set(P, r->gen[0]);
         select_buffers(r, 1);
         launch_timed(r, "raygen_debug", [&] { k_raygen_debug<<<grid, 256, 0, st>>>(P); });
         select_buffers(r, 0);
         TraceJob cam = camera_job(P, 1, false);
         launch_trace(r, "trace", &cam, nullptr, &P.counters[1 * C_STRIDE + C_WORK], S_SEGMENTS);
         launch_timed(r, "debug_shade", [&] { k_debug_shade<<<grid, 256, 0, st>>>(P); });
+        launch_timed(r, "accumulate", [&] { k_accumulate<<<grid, 256, 0, st>>>(P); });
     }
-    launch_timed(r, "accumulate", [&] { k_accumulate<<<grid, 256, 0, st>>>(P); });
     HNM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -207,10 +292,16 @@ void hnm_scene_destroy(hnm_scene* s) { scene_free(s); }
 void hnm_renderer_destroy(hnm_renderer* r) {
     if (!r) return;
     cudaSetDevice(r->scene->device);
+    if (r->rng_stream) cudaStreamSynchronize(r->rng_stream);
     if (r->stream) cudaStreamSynchronize(r->stream);
     r->timer.collect();
     for (auto p : r->allocs) cudaFree(p);
     for (auto e : r->marks) if (e) cudaEventDestroy(e);
+    for (auto& g : r->gen) {
+        if (g.ready) cudaEventDestroy(g.ready);
+        if (g.released) cudaEventDestroy(g.released);
+    }
+    if (r->rng_stream) cudaStreamDestroy(r->rng_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
 }
@@ -241,6 +332,8 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_TRACE_STATS")) r->trace_stats = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_NAMES")) r->per_bounce_names = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
+    if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
+    if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
     uint32_t ntiles = (height + sh.tile_rows - 1) / sh.tile_rows;
     uint32_t tiles_per_rank = (ntiles + sh.num_ranks - 1) / sh.num_ranks;
     r->padded_rows = tiles_per_rank * sh.tile_rows;  // equal on every rank (all-gather)
@@ -269,6 +362,14 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     auto bail = [&](int code) { hnm_renderer_destroy(r); return code; };
     cudaError_t ce = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
     if (ce != cudaSuccess) { delete r; return set_error(HNM_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); }
+    r->num_gen = (mode == HNM_MODE_PATHTRACING && r->overlap) ? 2 : 1;
+    if (r->num_gen == 2) {
+        // the generation kernel needs a whole SM's shared memory: give its CTAs priority whenever an SM drains
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        ce = cudaStreamCreateWithPriority(&r->rng_stream, cudaStreamNonBlocking, prio_hi);
+        if (ce != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); return bail(HNM_ERR_CUDA); }
+    }
     size_t cap = r->cap;
     auto& A = r->allocs;
     for (int b = 0; b < 2; b++) {
@@ -276,18 +377,33 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &r->thr_buf[b][k], cap))) return bail(rc);
         if ((rc = dev_alloc(A, &r->pid_buf[b], cap))) return bail(rc);
     }
-    for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &P.L[k], cap))) return bail(rc);
-    if ((rc = dev_alloc(A, &P.cursor, cap))) return bail(rc);
+    for (int s = 0; s < r->num_gen; s++) {
+        hnm_renderer::GenSet& g = r->gen[s];
+        for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &g.L[k], cap))) return bail(rc);
+        if ((rc = dev_alloc(A, &g.cursor, cap))) return bail(rc);
+        if (mode == HNM_MODE_PATHTRACING) {
+            for (int k = 0; k < 6; k++) if ((rc = dev_alloc(A, &g.ray[k], cap))) return bail(rc);
+            for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &g.thr[k], cap))) return bail(rc);
+            if ((rc = dev_alloc(A, &g.pid, cap))) return bail(rc);
+            if ((rc = dev_alloc(A, &g.tail, cap * RNG_TAIL))) return bail(rc);
+            if ((rc = dev_alloc(A, &g.q_ovf, cap))) return bail(rc);
+            if ((rc = dev_alloc(A, &g.ovf_counter, (size_t)4))) return bail(rc);
+        }
+        if (cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&g.released, cudaEventDisableTiming) != cudaSuccess) {
+            set_error(HNM_ERR_CUDA, "cudaEventCreate failed");
+            return bail(HNM_ERR_CUDA);
+        }
+    }
+    bind_gen_set(P, r->gen[0]);
     if ((rc = dev_alloc(A, &P.hit_t, cap))) return bail(rc);
     if ((rc = dev_alloc(A, &P.hit_u, cap))) return bail(rc);
     if ((rc = dev_alloc(A, &P.hit_v, cap))) return bail(rc);
     if ((rc = dev_alloc(A, &P.hit_id, cap))) return bail(rc);
     if (mode == HNM_MODE_PATHTRACING) {
-        if ((rc = dev_alloc(A, &P.tail, cap * RNG_TAIL))) return bail(rc);
         if ((rc = dev_alloc(A, &P.q_miss, cap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.q_delta, cap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.q_nee, cap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.q_ovf, cap))) return bail(rc);
         size_t scap = cap * std::max<uint32_t>(scene->num_emissions, 1);
         for (int k = 0; k < 3; k++) {
             if ((rc = dev_alloc(A, &P.ev_thr[k], cap))) return bail(rc);
@@ -311,7 +427,19 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     ce = cudaMemsetAsync(P.accum, 0, accum_n * sizeof(double), r->stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(P.stats, 0, S_COUNT * sizeof(unsigned long long), r->stream);
     if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
-        ce = cudaFuncSetAttribute(k_isaac_raygen, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_THREADS * 256 * (int)sizeof(uint64_t));
+        ce = cudaFuncSetAttribute(k_isaac_raygen, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_PATHS * 256 * (int)sizeof(uint64_t));
+    if (const char* e = getenv("HNM_CARVEOUT")) {
+        // experiment: the shared-memory carve-out the kernels that co-reside with k_isaac_raygen ask for
+        int c = atoi(e);
+        cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_miss, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_surf<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_surf<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_nee_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_batch_begin, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+    }
     if (ce != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("renderer init: ") + cudaGetErrorString(ce)); return bail(HNM_ERR_CUDA); }
     *out = r;
     return 0;
@@ -324,7 +452,11 @@ int hnm_render_passes(hnm_renderer* r, uint32_t sampling_first, uint32_t count) 
     uint32_t done = 0;
     while (done < count) {
         uint32_t b = std::min(r->max_batch, count - done);
-        int rc = run_batch(r, sampling_first + done, b);
+        // the batch after this one: the rest of this call, else (speculatively) the pass loop's next call --
+        // `sampling` only ever counts up by one (src/renderer.rs:32); a wrong guess costs one discarded generation
+        uint32_t left = count - done - b;
+        uint32_t nb = left > 0 ? std::min(r->max_batch, left) : (r->speculate ? b : 0u);
+        int rc = run_batch(r, sampling_first + done, b, sampling_first + done + b, nb);
         if (rc) return rc;
         done += b;
     }
@@ -509,7 +641,7 @@ int hnm_isaac64_batch(int device, const uint64_t* seeds, uint32_t n, uint32_t co
     HNM_TMP_UPLOAD(ds, seeds, (size_t)n * 4 * sizeof(uint64_t));
     HNM_CUDA(cudaMalloc(&dout, (size_t)n * count * sizeof(uint64_t)));
     if (count <= HNM_RNG_TAIL) {
-        size_t smem = (size_t)ISAAC_THREADS * 256 * sizeof(uint64_t);
+        size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
         HNM_CUDA(cudaFuncSetAttribute(k_isaac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_isaac_batch<<<148, ISAAC_THREADS, smem>>>(ds, n, count, dout);
     } else {

@@ -26,13 +26,32 @@
 namespace hnm {
 
 constexpr int RNG_TAIL = HNM_RNG_TAIL;  // u64 outputs kept per path
-constexpr int ISAAC_THREADS = 112;      // 112 x 2 KB = 224 KB of the 227 KB a CTA may use
+// ISAAC-64 seeding keeps the 2 KB `mem[]` of every path in shared memory: 112 paths x 2 KB = 224 KB of the 227 KB a CTA
+// may use, i.e. only 112 paths in flight per SM, each a ~12 k-instruction dependent chain.  With full warps that is
+// 3.5 warps per SM -- less than one per scheduler, pure latency (ncu, round 1: 35 % issue utilisation).  The paths
+// are therefore spread over MORE warps with only ISAAC_LANES active lanes each (16 -> 7 warps, ~2 per scheduler):
+// the same 112 chains, twice the warps to interleave.  Issue slots were idle anyway.
+#ifndef HNM_ISAAC_LANES
+#define HNM_ISAAC_LANES 32
+#endif
+#ifndef HNM_ISAAC_PATHS
+#define HNM_ISAAC_PATHS 112
+#endif
+constexpr int ISAAC_PATHS = HNM_ISAAC_PATHS;  // paths (columns of the shared-memory state) per CTA
+constexpr int ISAAC_LANES = HNM_ISAAC_LANES;
+constexpr int ISAAC_THREADS = (ISAAC_PATHS + ISAAC_LANES - 1) / ISAAC_LANES * 32;
+static_assert(ISAAC_LANES >= 1 && ISAAC_LANES <= 32, "bad ISAAC lane split");
+// path column of this thread inside the CTA, or -1 for a lane that idles
+__device__ __forceinline__ int isaac_slot() {
+    const int lane = threadIdx.x & 31;
+    const int slot = (int)(threadIdx.x >> 5) * ISAAC_LANES + lane;
+    return (lane < ISAAC_LANES && slot < ISAAC_PATHS) ? slot : -1;
+}
 constexpr int MAX_BOUNCE = 64;
 
 // counters[]: per bounce b (1-origin) eight slots
 enum { C_RAY = 0, C_MISS = 1, C_DELTA = 2, C_NEE = 3, C_EVENTS = 4, C_SHADOW = 5, C_WORK = 6, C_STRIDE = 8 };
-constexpr int OVF_COUNTER = (MAX_BOUNCE + 2) * C_STRIDE;
-constexpr int NUM_COUNTERS = OVF_COUNTER + 8;
+constexpr int NUM_COUNTERS = (MAX_BOUNCE + 2) * C_STRIDE + 8;
 // stats[] (u64)
 enum { S_PATHS = 0, S_SEGMENTS = 1, S_SHADOW = 2, S_RNG_FALLBACK = 3, S_NODES = 4, S_PRIMS = 5, S_COUNT = 8 };
 
@@ -59,7 +78,9 @@ struct RParams {
     uint64_t* tail;       // [RNG_TAIL][cap]
     // hits of the current bounce (queue order)
     double* hit_t; double* hit_u; double* hit_v; uint2* hit_id;
-    uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee; uint32_t* q_ovf;
+    uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee;
+    // exact-slow-path list of the generation set that L / cursor / tail belong to (see GenSet, hanamaru_b200.cu)
+    uint32_t* q_ovf; uint32_t* ovf_counter;
     // NEE events of the current bounce and their shadow rays (num_emissions per event, event-major)
     double* ev_thr[3]; double* ev_albedo[3]; double* ev_emission[3]; uint32_t* ev_pid;
     double* sray[6]; double* s_pos[3]; double* s_bsdf; double* s_g;
@@ -112,7 +133,7 @@ HNM_D PathCoord path_coord(const RParams& P, uint32_t p) {
 
 // `mem` is this thread's column of a [256][T] u64 array (shared memory: conflict-free for any per-lane
 // index because the bank depends only on the lane).  Outputs rsl[i] are handed to `sink`.
-template <int T, typename Sink>
+template <int T, int KEEP, typename Sink>
 __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, Sink sink) {
 #define MEM(i) mem[(i) * T]
     uint64_t a, b, c, d, e, f, g, h;
@@ -138,29 +159,39 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
     }
     // isaac64(): a = 0, b = 0, c = 1  ->  aa = 0, bb = 1
     uint64_t aa = 0, bb = 1;
-#define ISAAC_STEP(mixexpr, i, i2)                              \
+#define ISAAC_STEP(mixexpr, i, i2, SINK)                         \
     {                                                           \
         uint64_t x = MEM(i);                                    \
         aa = (mixexpr) + MEM(i2);                               \
         uint64_t y = MEM(((uint32_t)x >> 3) & 255u) + aa + bb;  \
         MEM(i) = y;                                             \
         bb = MEM(((uint32_t)y >> 11) & 255u) + x;               \
-        sink(i, bb);                                            \
+        SINK(i, bb);                                            \
     }
+#define ISAAC_NOSINK(i, v)
+    // only the last KEEP outputs (rsl[256-KEEP .. 255], the first KEEP words of the stream) are handed to `sink`
 #pragma unroll 1
     for (int base = 0; base < 128; base += 4) {
-        ISAAC_STEP(~(aa ^ (aa << 21)), base, base + 128)
-        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base + 129)
-        ISAAC_STEP(aa ^ (aa << 12), base + 2, base + 130)
-        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base + 131)
+        ISAAC_STEP(~(aa ^ (aa << 21)), base, base + 128, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base + 129, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa << 12), base + 2, base + 130, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base + 131, ISAAC_NOSINK)
     }
 #pragma unroll 1
-    for (int base = 128; base < 256; base += 4) {
-        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128)
-        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127)
-        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126)
-        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125)
+    for (int base = 128; base < 256 - KEEP; base += 4) {
+        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126, ISAAC_NOSINK)
+        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125, ISAAC_NOSINK)
     }
+#pragma unroll 1
+    for (int base = 256 - KEEP; base < 256; base += 4) {
+        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128, sink)
+        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127, sink)
+        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126, sink)
+        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125, sink)
+    }
+#undef ISAAC_NOSINK
 #undef ISAAC_STEP
 #undef MEM
 }
@@ -240,18 +271,17 @@ HNM_D void store_ray(const RParams& P, uint32_t q, D3 o, D3 d, D3 t, uint32_t pi
 
 __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_raygen(RParams P) {
     extern __shared__ uint64_t smem_isaac[];
-    const int tid = threadIdx.x;
-    uint64_t* mem = smem_isaac + tid;
+    const int slot = isaac_slot();
+    if (slot < 0) return;  // no CTA-wide synchronisation below
+    uint64_t* mem = smem_isaac + slot;
     const uint32_t N = P.N, cap = P.cap;
-    for (uint32_t p = blockIdx.x * ISAAC_THREADS + tid; p < N; p += gridDim.x * ISAAC_THREADS) {
+    for (uint32_t p = blockIdx.x * ISAAC_PATHS + slot; p < N; p += gridDim.x * ISAAC_PATHS) {
         PathCoord c = path_coord(P, p);
         uint64_t s0, s1, s2, s3;
         path_seed(c, P.sampling_first + c.pass, s0, s1, s2, s3);
         uint64_t* tail = P.tail + p;
         // outputs are consumed from rsl[255] downwards: word j of the stream = rsl[255 - j]
-        isaac64_seed<ISAAC_THREADS>(mem, s0, s1, s2, s3, [&](int i, uint64_t v) {
-            if (i >= 256 - RNG_TAIL) tail[(size_t)(255 - i) * cap] = v;
-        });
+        isaac64_seed<ISAAC_PATHS, RNG_TAIL>(mem, s0, s1, s2, s3, [&](int i, uint64_t v) { tail[(size_t)(255 - i) * cap] = v; });
         // sample_on_lens (src/camera.rs:66-81): rejection loop over pairs of the stream
         int cur = 0;
         double sqx = 0.0, sqy = 0.0;
@@ -267,7 +297,7 @@ __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_raygen(RParams P) {
         P.L[0][p] = 0.0; P.L[1][p] = 0.0; P.L[2][p] = 0.0;
         if (!ok || cur + 2 * (int)(P.sc.bounce_limit - 1) > P.tail_k) {
             // the stored tail is too short for this path: exact slow path (k_rng_overflow fills the slot)
-            uint32_t slot = atomicAdd(&P.counters[OVF_COUNTER], 1u);
+            uint32_t slot = atomicAdd(P.ovf_counter, 1u);
             P.q_ovf[slot] = p;
             continue;
         }
@@ -276,14 +306,18 @@ __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_raygen(RParams P) {
         store_ray(P, p, o, d, splat(1.0), p);
         P.cursor[p] = (uint8_t)cur;
     }
-    if (blockIdx.x == 0 && tid == 0) {
-        P.counters[1 * C_STRIDE + C_RAY] = N;
-        atomicAdd(&P.stats[S_PATHS], (unsigned long long)N);
-    }
+}
+
+// First kernel of a path-tracing batch on the renderer's stream.  The generation kernels above may have run
+// long before (on the RNG stream, overlapped with the previous batch), so they do not touch `counters` / `stats`.
+__global__ void k_batch_begin(RParams P) {
+    P.counters[1 * C_STRIDE + C_RAY] = P.N;
+    atomicAdd(&P.stats[S_PATHS], (unsigned long long)P.N);
+    atomicAdd(&P.stats[S_RNG_FALLBACK], (unsigned long long)*P.ovf_counter);
 }
 
 __global__ void k_rng_overflow(RParams P) {
-    uint32_t n = P.counters[OVF_COUNTER];
+    uint32_t n = *P.ovf_counter;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t p = P.q_ovf[i];
         PathCoord c = path_coord(P, p);
@@ -307,7 +341,6 @@ __global__ void k_rng_overflow(RParams P) {
         store_ray(P, p, o, d, splat(1.0), p);
         P.cursor[p] = 0;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&P.stats[S_RNG_FALLBACK], (unsigned long long)n);
 }
 
 // DebugRenderer: pinhole ray, no RNG (src/camera.rs:98-107, src/renderer.rs:117)
@@ -642,10 +675,12 @@ __global__ void k_deinterleave(const double* gathered, double* full, uint32_t W,
 // ------------------------------------------------------------------------------------ batch (unit parity) kernels
 __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_batch(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
     extern __shared__ uint64_t smem_isaac[];
-    uint64_t* mem = smem_isaac + threadIdx.x;
-    for (uint32_t p = blockIdx.x * ISAAC_THREADS + threadIdx.x; p < n; p += gridDim.x * ISAAC_THREADS) {
+    const int slot = isaac_slot();
+    if (slot < 0) return;
+    uint64_t* mem = smem_isaac + slot;
+    for (uint32_t p = blockIdx.x * ISAAC_PATHS + slot; p < n; p += gridDim.x * ISAAC_PATHS) {
         uint64_t* o = out + (size_t)p * count;
-        isaac64_seed<ISAAC_THREADS>(mem, seeds[4 * p], seeds[4 * p + 1], seeds[4 * p + 2], seeds[4 * p + 3], [&](int i, uint64_t v) {
+        isaac64_seed<ISAAC_PATHS, RNG_TAIL>(mem, seeds[4 * p], seeds[4 * p + 1], seeds[4 * p + 2], seeds[4 * p + 3], [&](int i, uint64_t v) {
             int j = 255 - i;
             if (j < (int)count) o[j] = v;
         });
