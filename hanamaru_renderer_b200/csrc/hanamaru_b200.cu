@@ -78,6 +78,9 @@ struct hnm_renderer {
     bool speculate = true;         // HNM_RNG_SPECULATE=0: no prefetch across hnm_render_passes calls
     uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
+    // NEE accepts a shadow hit iff |hit - light sample|^2 < 4 * offset (src/vector.rs:89-91, src/renderer.rs:282):
+    // only hits within sqrt(4 * offset) of the sample's distance matter.  Slack covers that plus the f32 roundings.
+    float tmax_slack = 0.0f;
     int trace_blocks_per_sm = HNM_TRACE_MIN_BLOCKS;  // persistent CTAs per SM = what the register budget allows
     cudaEvent_t marks[16] = {};
 };
@@ -165,6 +168,7 @@ TraceJob shadow_job(const RParams& P, int bounce) {
     for (int k = 0; k < 6; k++) j.ray[k] = P.sray[k];
     j.hit_t = P.sh_t; j.hit_u = P.sh_u; j.hit_v = P.sh_v; j.hit_id = P.sh_id;
     j.count = &P.counters[bounce * C_STRIDE + C_SHADOW];
+    j.tmax = P.s_tmax;
     return j;
 }
 
@@ -185,6 +189,7 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     A.stats = r->P.stats;
     A.stat_segments = stat_segments;
     A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
+    A.tmax_slack = r->tmax_slack;
     const int grid = r->sm_count * r->trace_blocks_per_sm;
     DScene sc = r->P.sc;
     cudaStream_t st = r->stream;
@@ -346,6 +351,8 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     cudaDeviceProp prop;
     HNM_CUDA(cudaGetDeviceProperties(&prop, scene->device));
     r->sm_count = prop.multiProcessorCount;
+    r->tmax_slack = (float)(std::sqrt(4.0 * scene->config.offset) * 1.05 + 1e-5 * (double)scene->d.scene_r + 1e-6);
+    if (const char* e = getenv("HNM_SHADOW_BOUNDED")) { if (atoi(e) == 0) r->tmax_slack = 3.0e38f; }  // A/B: unbounded closest hit
     size_t per_pass = (size_t)P.npix * P.spp;
     if (mode != HNM_MODE_PATHTRACING) max_batch = 1;
     if (max_batch == 0) {
@@ -415,6 +422,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         for (int k = 0; k < 6; k++) if ((rc = dev_alloc(A, &P.sray[k], scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.s_bsdf, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.s_g, scap))) return bail(rc);
+        if ((rc = dev_alloc(A, &P.s_tmax, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.sh_t, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.sh_u, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.sh_v, scap))) return bail(rc);

@@ -84,6 +84,7 @@ struct RParams {
     // NEE events of the current bounce and their shadow rays (num_emissions per event, event-major)
     double* ev_thr[3]; double* ev_albedo[3]; double* ev_emission[3]; uint32_t* ev_pid;
     double* sray[6]; double* s_pos[3]; double* s_bsdf; double* s_g;
+    float* s_tmax;        // distance from the shading point to the light sample: the shadow query is bounded (k_trace)
     double* sh_t; double* sh_u; double* sh_v; uint2* sh_id;
     uint32_t* counters;
     unsigned long long* stats;
@@ -371,6 +372,36 @@ HNM_D uint32_t queue_alloc(bool pred, uint32_t* counter) {
     return base + __popc(mask & ((1u << lane) - 1u));
 }
 
+// Slot in the next ray queue for every thread of the CTA with `pred`, grouped by `key` (0..7) inside the CTA's
+// contiguous run of slots: the rays a CTA emits come from neighbouring paths (similar origins); ordering them by
+// direction octant makes the warps of the next k_trace launch pick up rays that also descend the tree the same
+// way.  One global atomic per CTA.  All threads of the CTA must call this (two barriers).
+#ifndef HNM_SHADE_OCTANT_SORT
+#define HNM_SHADE_OCTANT_SORT 1
+#endif
+HNM_D uint32_t queue_alloc_grouped(bool pred, uint32_t key, uint32_t* counter) {
+    __shared__ uint32_t s_cnt[8], s_base[8], s_gbase;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 8) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t k = pred ? key : 8u;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, k);
+    const int leader = __ffs(peers) - 1;
+    uint32_t woff = 0;
+    if (pred && lane == leader) woff = atomicAdd(&s_cnt[k], (uint32_t)__popc(peers));
+    woff = __shfl_sync(0xFFFFFFFFu, woff, leader);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int j = 0; j < 8; j++) { s_base[j] = tot; tot += s_cnt[j]; }
+        s_gbase = tot ? atomicAdd(counter, tot) : 0u;
+    }
+    __syncthreads();
+    return pred ? s_gbase + s_base[k] + woff + rank : 0u;
+}
+HNM_D uint32_t direction_octant(D3 d) { return (signbit_(d.x) ? 1u : 0u) | (signbit_(d.y) ? 2u : 0u) | (signbit_(d.z) ? 4u : 0u); }
+
 HNM_D D3 load_ray_o(const RParams& P, uint32_t q) { return d3(P.rin[0][q], P.rin[1][q], P.rin[2][q]); }
 HNM_D D3 load_ray_d(const RParams& P, uint32_t q) { return d3(P.rin[3][q], P.rin[4][q], P.rin[5][q]); }
 HNM_D D3 load_thr(const RParams& P, uint32_t q) { return d3(P.tin[0][q], P.tin[1][q], P.tin[2][q]); }
@@ -414,7 +445,7 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce) {
     const uint32_t nl = P.sc.num_emissions;
     uint32_t shadow_rays = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t n_round = (n + 255u) & ~255u;  // CTA-uniform trip count (blockDim.x == 256): barriers inside
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         bool alive = false, event = false;
         D3 no = splat(0.0), nd = splat(0.0), nthr = splat(0.0), thr = splat(0.0), view = splat(0.0);
@@ -455,7 +486,11 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce) {
             }
             // None: `break` before the emission is added (src/renderer.rs:190-193)
         }
+#if HNM_SHADE_OCTANT_SORT
+        uint32_t q2 = queue_alloc_grouped(alive, direction_octant(nd), &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
+#else
         uint32_t q2 = queue_alloc(alive, &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
+#endif
         if (alive) store_ray(P, q2, no, nd, nthr, pid);
         if (NEE) {
             uint32_t ev = queue_alloc(event, &P.counters[bounce * C_STRIDE + C_EVENTS]);
@@ -483,6 +518,7 @@ __global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce) {
                     P.sray[3][s] = shadow_dir.x; P.sray[4][s] = shadow_dir.y; P.sray[5][s] = shadow_dir.z;
                     P.s_pos[0][s] = s_position.x; P.s_pos[1][s] = s_position.y; P.s_pos[2][s] = s_position.z;
                     P.s_g[s] = (dot_0 * dot_l) / distance_pow2;
+                    P.s_tmax[s] = (float)__dsqrt_rn(distance_pow2);
                     P.s_bsdf[s] = bsdf(pm, view, sp.normal, shadow_dir);
                 }
             }

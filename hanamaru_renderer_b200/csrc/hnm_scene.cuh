@@ -272,12 +272,12 @@ class SceneBuilder {
                 acc.grow(bb[b]);
                 c += cnt[b];
                 if (c == 0 || right_cnt[b + 1] == 0) continue;
-                double cost = 1.0 + (half_area(acc) * (double)c + right_area[b + 1] * (double)right_cnt[b + 1]) / parent_area;
+                double cost = 1.0 + sah_ct * (half_area(acc) * (double)c + right_area[b + 1] * (double)right_cnt[b + 1]) / parent_area;
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
             }
         }
-        const double leaf_cost = (double)n;  // one pre-test per triangle ~ one node step
-        if (all_tri && n <= 7 && (best_axis < 0 || leaf_cost <= best_cost)) return make_leaf();
+        const double leaf_cost = sah_ct * (double)n;  // cost of one triangle pre-test in node steps
+        if (all_tri && n <= sah_max_leaf && (best_axis < 0 || leaf_cost <= best_cost)) return make_leaf();
         size_t mid;
         if (best_axis >= 0) {
             double ext = cb.hi[best_axis] - cb.lo[best_axis], base = cb.lo[best_axis];
@@ -298,7 +298,11 @@ class SceneBuilder {
         int32_t l1 = sah_rec(prims, mid, hi, order, b1);
         return make_inner(l0, b0, l1, b1, slot);
     }
+    double sah_ct = 1.0;
+    size_t sah_max_leaf = 7;
     int32_t build_sah(BoxD& out) {
+        if (const char* e = getenv("HNM_SAH_CT")) { double v = atof(e); if (v > 0.0) sah_ct = v; }
+        if (const char* e = getenv("HNM_SAH_MAXLEAF")) { int v = atoi(e); if (v >= 1 && v <= 7) sah_max_leaf = (size_t)v; }
         std::vector<Prim> prims;
         prims.reserve(tris.size() + d_->num_elements);
         for (size_t g = 0; g < tris.size(); g++) {

@@ -31,6 +31,16 @@ namespace hnm {
 #ifndef HNM_TRACE_REFILL
 #define HNM_TRACE_REFILL 20
 #endif
+#ifndef HNM_TRACE_TOPREG
+#define HNM_TRACE_TOPREG 0      /* keep the stack top in a register */
+#endif
+#ifndef HNM_TRACE_NODE_STEPS
+#define HNM_TRACE_NODE_STEPS 3  /* max node steps per scheduling vote */
+#endif
+#ifndef HNM_TRACE_LEAF_STEPS
+#define HNM_TRACE_LEAF_STEPS 2  /* max leaf steps per scheduling vote */
+#endif
+
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_REFILL = HNM_TRACE_REFILL;  // refetch when fewer lanes than this are still traversing
 
@@ -38,6 +48,7 @@ struct TraceJob {
     const double* ray[6];  // origin xyz, direction xyz (SoA)
     double* hit_t; double* hit_u; double* hit_v; uint2* hit_id;
     const uint32_t* count;     // rays in this list (device memory)
+    const float* tmax;         // optional: bounded query, see k_trace (null = closest hit along the whole ray)
     // classification of camera-path hits into shading queues (null for shadow rays)
     uint32_t* cnt_miss; uint32_t* cnt_delta; uint32_t* cnt_nee;
     uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee;
@@ -49,6 +60,7 @@ struct TraceArgs {
     int njobs;
     int stat_segments;              // stats index that receives job[0]'s ray count, or -1
     int stat_nodes, stat_prims;
+    float tmax_slack;               // half-width of the window around tmax[] inside which the exact closest hit matters
 };
 
 HNM_D void warp_queue_push(bool pred, uint32_t* counter, uint32_t* queue, uint32_t value, int lane) {
@@ -111,6 +123,10 @@ HNM_D bool tri_pretest(const float4* __restrict__ tf, const RayF& R, float& best
     return true;
 }
 
+// `cur` of a lane without a ray: a LEAF_NONE link, so that "holds a node" is cur >= 0 and "holds a leaf" is
+// cur < 0 && cur != TRACE_IDLE -- two ballots per scheduling round instead of three
+constexpr int32_t TRACE_IDLE = ~(int32_t)((uint32_t)LEAF_NONE << 29);
+
 template <bool STATS>
 __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(DScene sc, TraceArgs A) {
     const int lane = threadIdx.x & 31;
@@ -119,16 +135,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     const uint32_t ntot = n0 + n1;
     const float W = 4.76837158203125e-07f;  // 2^-21, see hnm_device.cuh: trace()
 
+    // traversal stack: the top entry lives in a register (`top`), the rest in local memory -- a pop hands `top` to
+    // `cur` at once and the reload of the next entry is off the critical path (ncu, round 1: the dependent local load
+    // `cur = stack[--sp]` in front of the node fetch was the most-sampled line of the kernel)
     int32_t stack[HNM_STACK];
-    int sp = 0;
-    int32_t cur = 0;
-    bool has_ray = false, pending = false;
+    int sp = 0;          // entries on the stack INCLUDING `top`
+    int32_t top = 0;
+    int32_t cur = TRACE_IDLE;
+    bool pending = false;
     uint32_t idx = 0;
     D3 o = splat(0.0), dir = splat(0.0);
     RayF R;
     R.ox = R.oy = R.oz = R.ix = R.iy = R.iz = R.rx = R.ry = R.rz = 0.f; R.K = 0.f; R.t0 = 0.f;
     double t0 = 0.0;
     float best_ub = 3.0e38f;
+    float t_occ = -3.0e38f;  // shadow rays: a certain hit closer than this ends the ray (see TraceJob::tmax)
     Hit best;
     best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
     // candidate triangles awaiting the exact test (newest first)
@@ -145,20 +166,43 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
         if (STATS) n_prims++;                                      \
         tri_test(tr_, (g), o, dir, best);                          \
     }
+#if HNM_TRACE_TOPREG
+#define HNM_POP()                                                  \
+    {                                                              \
+        if (sp == 0) { cur = TRACE_IDLE; pending = true; }         \
+        else {                                                     \
+            cur = top;                                             \
+            sp--;                                                  \
+            if (sp > 0) top = stack[sp - 1];                       \
+        }                                                          \
+    }
+#define HNM_PUSH(v)                                                \
+    {                                                              \
+        if (sp > 0) stack[sp - 1] = top;                           \
+        top = (v);                                                 \
+        sp++;                                                      \
+    }
+#else
+#define HNM_POP()                                                  \
+    {                                                              \
+        if (sp == 0) { cur = TRACE_IDLE; pending = true; }         \
+        else cur = stack[--sp];                                    \
+    }
+#define HNM_PUSH(v) { stack[sp++] = (v); }
+#endif
 
     for (;;) {
         // ---- converged: confirm candidates of finished rays in f64, retire them ----------------------------
         {
+            int cls = -1;
             if (pending) {
                 // the exact closest hit is among the candidates whose lower bound does not exceed the bound
                 if (ncand > 0 && l0 <= best_ub) HNM_EXACT(c0)
                 if (ncand > 1 && l1_ <= best_ub) HNM_EXACT(c1)
                 if (ncand > 2 && l2 <= best_ub) HNM_EXACT(c2)
                 if (ncand > 3 && l3 <= best_ub) HNM_EXACT(c3)
+                if (ncand < 0) { best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0; }  // occluded shadow ray
                 ncand = 0;
-            }
-            int cls = -1;
-            if (pending) {
                 const bool j1 = idx >= n0;
                 const TraceJob& J = A.job[j1 ? 1 : 0];
                 const uint32_t q = j1 ? idx - n0 : idx;
@@ -183,14 +227,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
         }
         // ---- converged: fetch new rays -----------------------------------------------------------------------
         {
-            unsigned need = __ballot_sync(0xFFFFFFFFu, !has_ray);
+            unsigned need = __ballot_sync(0xFFFFFFFFu, cur == TRACE_IDLE);
             if (need) {
                 int leader = __ffs(need) - 1;
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(A.work, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
                 more = base + (uint32_t)__popc(need) < ntot;
-                if (!has_ray) {
+                if (cur == TRACE_IDLE) {
                     idx = base + __popc(need & ((1u << lane) - 1u));
                     if (idx < ntot) {
                         const bool j1 = idx >= n0;
@@ -200,9 +244,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         dir = d3(J.ray[3][q], J.ray[4][q], J.ray[5][q]);
                         best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
                         best_ub = 3.0e38f;
+                        t_occ = -3.0e38f;
                         ncand = 0;
                         t0 = 0.0;
-                        has_ray = true;
                         sp = 0;
                         cur = 0;
                         lk = 0;
@@ -211,8 +255,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                             double dist;
                             bool h = aabb_intersect_ray(sc.bounds_lo[0], sc.bounds_lo[1], sc.bounds_lo[2], sc.bounds_hi[0], sc.bounds_hi[1],
                                                         sc.bounds_hi[2], o, dir, &dist);
-                            if (!h) { has_ray = false; pending = true; }
+                            if (!h) { cur = TRACE_IDLE; pending = true; }
                             else if (dist > 0.0 && dist < sc.inf) t0 = dist * (1.0 - 1e-6);
+                        } else if (J.tmax) {
+                            // Bounded query (NEE shadow rays): the caller only looks at the closest hit if it lies within
+                            // `slack` of distance tmax[q] along the ray (src/renderer.rs:282, Vector3::approximately).
+                            // Nothing beyond tmax + slack can be that hit, and a certain hit before tmax - slack means the
+                            // closest hit is not it either: the ray ends at once and reports "no hit".
+                            const float D = J.tmax[q];
+                            best_ub = D + A.tmax_slack;
+                            t_occ = D - A.tmax_slack;
                         }
                         R.ox = (float)(o.x + dir.x * t0); R.oy = (float)(o.y + dir.y * t0); R.oz = (float)(o.z + dir.z * t0);
                         R.ix = (float)(1.0 / dir.x); R.iy = (float)(1.0 / dir.y); R.iz = (float)(1.0 / dir.z);
@@ -223,7 +275,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                     }
                 }
             }
-            if (__ballot_sync(0xFFFFFFFFu, has_ray || pending) == 0) break;
+            if (__ballot_sync(0xFFFFFFFFu, cur != TRACE_IDLE || pending) == 0) break;
         }
         // ---- traverse (f32) until too few lanes are left -----------------------------------------------------
         // Majority-vote scheduling.  Each iteration every lane is in one of two states: it holds a NODE (cur >= 0)
@@ -233,47 +285,51 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
         // independent thread scheduling a per-lane `while (has_ray)` never reconverges, and a strict while-while
         // loop (all lanes descend to a leaf, then all test it) ran at 4 of 32 lanes per instruction on the
         // incoherent bounces because the longest descent of the warp sets the pace (ncu, round 1).
-        unsigned act = __ballot_sync(0xFFFFFFFFu, has_ray);
-        while (act) {
-            bool done = false;
-            const bool is_node = has_ray && cur >= 0;
+        for (;;) {
+            const bool is_node = cur >= 0;
             const unsigned nm = __ballot_sync(0xFFFFFFFFu, is_node);
-            if (2 * __popc(nm) >= __popc(act)) {
-                if (is_node) {
-                    const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
-                    float4 m0 = __ldg(np), m1 = __ldg(np + 1), m2 = __ldg(np + 2);
-                    int4 m3 = __ldg(reinterpret_cast<const int4*>(np + 3));
-                    if (STATS) n_nodes++;
-                    float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
-                    float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
-                    float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
-                    float tmin0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
-                    float tmax0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
-                    float g0 = (m1.z - R.ox) * R.ix, e0 = (m2.y - R.ox) * R.ix;
-                    float g1 = (m1.w - R.oy) * R.iy, e1 = (m2.z - R.oy) * R.iy;
-                    float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
-                    float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
-                    float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
-                    float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
-                    float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
-                    bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= best_ub);
-                    bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= best_ub);
-                    if (h0 && h1) {
-                        bool swap = lo1 < lo0;
-                        if (sp < HNM_STACK) stack[sp++] = swap ? m3.x : m3.y;
-                        cur = swap ? m3.y : m3.x;
-                    } else if (h0) {
-                        cur = m3.x;
-                    } else if (h1) {
-                        cur = m3.y;
-                    } else if (sp == 0) {
-                        done = true;
-                    } else {
-                        cur = stack[--sp];
+            const unsigned lm = __ballot_sync(0xFFFFFFFFu, cur < 0 && cur != TRACE_IDLE);
+            const int nn = __popc(nm), nl = __popc(lm);
+            if (nn + nl == 0 || (more && nn + nl < TRACE_REFILL)) break;  // too few lanes left: refill (lanes keep their state)
+            if (nn >= nl) {
+                // node phase: HNM_TRACE_NODE_STEPS steps per vote, unrolled, no ballot in between (lanes that reach a
+                // leaf early idle for the rest of the phase; re-voting after every step cost more than it saved)
+#pragma unroll
+                for (int rep = 0; rep < HNM_TRACE_NODE_STEPS; rep++) {
+                    if (cur >= 0) {
+                        const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+                        float4 m0 = __ldg(np), m1 = __ldg(np + 1), m2 = __ldg(np + 2);
+                        int2 m3 = __ldg(reinterpret_cast<const int2*>(np + 3));
+                        if (STATS) n_nodes++;
+                        float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
+                        float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
+                        float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
+                        float tmin0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+                        float tmax0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+                        float g0 = (m1.z - R.ox) * R.ix, e0 = (m2.y - R.ox) * R.ix;
+                        float g1 = (m1.w - R.oy) * R.iy, e1 = (m2.z - R.oy) * R.iy;
+                        float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
+                        float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
+                        float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
+                        float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
+                        float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
+                        const bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= best_ub);
+                        const bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= best_ub);
+                        const bool swap = lo1 < lo0;
+                        lk = 0;
+                        if (h0 || h1) {
+                            // near child next; the far one (if both are hit) becomes the new stack top
+                            cur = (h0 && !(h1 && swap)) ? m3.x : m3.y;
+                            if (h0 && h1 && sp < HNM_STACK) HNM_PUSH(swap ? m3.x : m3.y)
+                        } else {
+                            HNM_POP()
+                        }
                     }
-                    lk = 0;
                 }
-            } else if (has_ray && !is_node) {
+            } else {
+#pragma unroll
+              for (int rep = 0; rep < HNM_TRACE_LEAF_STEPS; rep++) {
+                if (cur < 0 && cur != TRACE_IDLE) {
                 // one primitive of the leaf this lane holds
                 const int kind = leaf_kind(cur);
                 const uint32_t first = leaf_first(cur);
@@ -306,21 +362,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                     cuboid_test(sc.elements[first], first, sc.elements, o, dir, best);
                     best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
                 }
-                if (leaf_done) {
+                if (best_ub < t_occ) {
+                    // bounded query: something certainly lies in front of the point the caller asked about
+                    ncand = -1;
+                    cur = TRACE_IDLE;
+                    pending = true;
+                } else if (leaf_done) {
                     lk = 0;
-                    if (sp == 0) done = true;
-                    else cur = stack[--sp];
+                    HNM_POP()
                 }
+                }
+              }
             }
-            if (done) {
-                has_ray = false;
-                pending = true;
-            }
-            act = __ballot_sync(0xFFFFFFFFu, has_ray);
-            if (more && __popc(act) < TRACE_REFILL) break;  // too few lanes left: refill (lanes keep their state)
         }
     }
 #undef HNM_EXACT
+#undef HNM_POP
+#undef HNM_PUSH
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.stat_segments >= 0) atomicAdd(&A.stats[A.stat_segments], (unsigned long long)n0);
     if (STATS) {
         for (int s = 16; s > 0; s >>= 1) { n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, s); n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, s); }
