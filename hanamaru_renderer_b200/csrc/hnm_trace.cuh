@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                 const bool j1 = idx >= n0;
                 const TraceJob& J = A.job[j1 ? 1 : 0];
                 const uint32_t q = j1 ? idx - n0 : idx;
-                J.hit_t[q] = best.t; J.hit_u[q] = best.u; J.hit_v[q] = best.v;
-                J.hit_id[q] = make_uint2(best.kind, best.id);
+                __stcs(J.hit_t + q, best.t); __stcs(J.hit_u + q, best.u); __stcs(J.hit_v + q, best.v);
+                __stcs(J.hit_id + q, make_uint2(best.kind, best.id));
                 if (!j1 && J.q_miss) {
                     if (best.kind == LEAF_NONE) cls = 0;
                     else {
@@ -240,8 +240,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         const bool j1 = idx >= n0;
                         const TraceJob& J = A.job[j1 ? 1 : 0];
                         const uint32_t q = j1 ? idx - n0 : idx;
-                        o = d3(J.ray[0][q], J.ray[1][q], J.ray[2][q]);
-                        dir = d3(J.ray[3][q], J.ray[4][q], J.ray[5][q]);
+                        // streaming (evict-first) loads and stores for the ray / hit records: the L1 is for the tree
+                        o = d3(__ldcs(J.ray[0] + q), __ldcs(J.ray[1] + q), __ldcs(J.ray[2] + q));
+                        dir = d3(__ldcs(J.ray[3] + q), __ldcs(J.ray[4] + q), __ldcs(J.ray[5] + q));
                         best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
                         best_ub = 3.0e38f;
                         t_occ = -3.0e38f;
@@ -262,7 +263,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                             // `slack` of distance tmax[q] along the ray (src/renderer.rs:282, Vector3::approximately).
                             // Nothing beyond tmax + slack can be that hit, and a certain hit before tmax - slack means the
                             // closest hit is not it either: the ray ends at once and reports "no hit".
-                            const float D = J.tmax[q];
+                            const float D = __ldcs(J.tmax + q);
                             best_ub = D + A.tmax_slack;
                             t_occ = D - A.tmax_slack;
                         }
