@@ -78,6 +78,7 @@ struct hnm_renderer {
     bool speculate = true;         // HNM_RNG_SPECULATE=0: no prefetch across hnm_render_passes calls
     uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
+    CandLists cand = {};           // candidate lists of the rays in flight: camera rays [0, cap), shadow rays [cap, cap + scap)
     // NEE accepts a shadow hit iff |hit - light sample|^2 < 4 * offset (src/vector.rs:89-91, src/renderer.rs:282):
     // only hits within sqrt(4 * offset) of the sample's distance matter.  Slack covers that plus the f32 roundings.
     float tmax_slack = 0.0f;
@@ -155,6 +156,7 @@ TraceJob camera_job(const RParams& P, int bounce, bool classify) {
     for (int k = 0; k < 6; k++) j.ray[k] = P.rin[k];
     j.hit_t = P.hit_t; j.hit_u = P.hit_u; j.hit_v = P.hit_v; j.hit_id = P.hit_id;
     j.count = &P.counters[bounce * C_STRIDE + C_RAY];
+    j.slot0 = 0;
     if (classify) {
         j.cnt_miss = &P.counters[bounce * C_STRIDE + C_MISS]; j.cnt_delta = &P.counters[bounce * C_STRIDE + C_DELTA];
         j.cnt_nee = &P.counters[bounce * C_STRIDE + C_NEE];
@@ -169,6 +171,7 @@ TraceJob shadow_job(const RParams& P, int bounce) {
     j.hit_t = P.sh_t; j.hit_u = P.sh_u; j.hit_v = P.sh_v; j.hit_id = P.sh_id;
     j.count = &P.counters[bounce * C_STRIDE + C_SHADOW];
     j.tmax = P.s_tmax;
+    j.slot0 = P.cap;  // the shadow rays' candidate lists follow the camera rays'
     return j;
 }
 
@@ -190,11 +193,18 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     A.stat_segments = stat_segments;
     A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
     A.tmax_slack = r->tmax_slack;
+    A.cand = r->cand;
     const int grid = r->sm_count * r->trace_blocks_per_sm;
+    const int cgrid = r->sm_count * 8;
     DScene sc = r->P.sc;
     cudaStream_t st = r->stream;
-    if (r->trace_stats) launch_timed(r, name, [&] { k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
-    else launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
+    if (r->trace_stats) {
+        launch_timed(r, name, [&] { k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
+        launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, A); });
+    } else {
+        launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
+        launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, A); });
+    }
 }
 
 // One batch of passes.  (next_first, next_batch) is the batch the caller expects to run after this one (0 = none):
@@ -428,6 +438,15 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         if ((rc = dev_alloc(A, &P.sh_v, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.sh_id, scap))) return bail(rc);
     }
+    {
+        size_t nl = cap + (mode == HNM_MODE_PATHTRACING ? cap * std::max<uint32_t>(scene->num_emissions, 1) : 0);
+        if (nl >= (1ull << 32)) { set_error(HNM_ERR_INVALID, "too many rays in flight for 32-bit list slots"); return bail(HNM_ERR_INVALID); }
+        r->cand.stride = (uint32_t)nl;
+        if ((rc = dev_alloc(A, &r->cand.id, nl * TRACE_CAND))) return bail(rc);
+        if ((rc = dev_alloc(A, &r->cand.lo, nl * TRACE_CAND))) return bail(rc);
+        if ((rc = dev_alloc(A, &r->cand.n, nl))) return bail(rc);
+        if ((rc = dev_alloc(A, &r->cand.ub, nl))) return bail(rc);
+    }
     if ((rc = dev_alloc(A, &P.counters, (size_t)NUM_COUNTERS))) return bail(rc);
     if ((rc = dev_alloc(A, &P.stats, (size_t)S_COUNT))) return bail(rc);
     size_t accum_n = (size_t)r->padded_rows * width * 3;
@@ -603,6 +622,10 @@ int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_h
     auto cleanup = [&] { for (auto p : tmp) cudaFree(p); };
     int rc = 0;
     double* ray[6]; double *ht, *hu, *hv; uint2* hid; uint32_t* cnt; hnm_hit* dh; unsigned long long* dstats;
+    CandLists cl;
+    cl.stride = n;
+    if ((rc = dev_alloc(tmp, &cl.id, (size_t)n * TRACE_CAND)) || (rc = dev_alloc(tmp, &cl.lo, (size_t)n * TRACE_CAND)) ||
+        (rc = dev_alloc(tmp, &cl.n, (size_t)n)) || (rc = dev_alloc(tmp, &cl.ub, (size_t)n))) { cleanup(); return rc; }
     for (int k = 0; k < 6; k++) if ((rc = dev_alloc(tmp, &ray[k], (size_t)n))) { cleanup(); return rc; }
     if ((rc = dev_alloc(tmp, &ht, (size_t)n)) || (rc = dev_alloc(tmp, &hu, (size_t)n)) || (rc = dev_alloc(tmp, &hv, (size_t)n)) ||
         (rc = dev_alloc(tmp, &hid, (size_t)n)) || (rc = dev_alloc(tmp, &cnt, (size_t)16)) || (rc = dev_alloc(tmp, &dh, (size_t)n)) ||
@@ -626,7 +649,9 @@ int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_h
     A.work = cnt + 1;
     A.stats = dstats;
     A.stat_segments = -1; A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
-    k_trace<false><<<148 * 4, TRACE_THREADS>>>(scene->d, A);
+    A.cand = cl;
+    k_trace<false><<<148 * HNM_TRACE_MIN_BLOCKS, TRACE_THREADS>>>(scene->d, A);
+    k_confirm<false><<<148 * 8, 256>>>(scene->d, A);
     RayPtrs rp;
     for (int k = 0; k < 6; k++) rp.p[k] = ray[k];
     k_hits_to_abi<<<592, 256>>>(scene->d, rp, ht, hu, hv, hid, n, dh);

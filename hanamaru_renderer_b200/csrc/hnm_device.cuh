@@ -128,6 +128,8 @@ struct DScene {
     const uint32_t* tri_elem;  // element id per triangle
     const uint32_t* tri_face;  // face index inside its mesh
     const DElement* elements;
+    const float4* elemf;       // 4 x float4 per element for the f32 pre-tests (hnm_trace.cuh): sphere = (centre, radius);
+                               // cuboid = box rounded outward (lo, hi), box rounded inward (lo, hi)
     const DMaterial* materials;
     const DImage* images;
     const DImage* sky_faces;  // px nx py ny pz nz (device memory: indexed at run time)

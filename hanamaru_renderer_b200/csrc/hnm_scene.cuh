@@ -496,6 +496,31 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
         s->elem_surface[i] = desc->materials[e.material].surface;
     }
     if ((rc = upload(s, els, &s->d.elements))) return bail(rc);
+    {
+        std::vector<float4> ef((size_t)desc->num_elements * 4, make_float4(NAN, NAN, NAN, NAN));
+        for (uint32_t i = 0; i < desc->num_elements; i++) {
+            const hnm_element& e = desc->elements[i];
+            if (e.kind == HNM_ELEM_SPHERE) {
+                ef[4 * i] = make_float4((float)e.a.x, (float)e.a.y, (float)e.a.z, (float)e.radius);
+            } else if (e.kind == HNM_ELEM_CUBOID) {
+                const double lo[3] = {e.a.x, e.a.y, e.a.z}, hi[3] = {e.b.x, e.b.y, e.b.z};
+                float ol[3], oh[3], il[3], ih[3];
+                bool inner_ok = true;
+                for (int k = 0; k < 3; k++) {
+                    ol[k] = f32_down(lo[k] - b.pad); oh[k] = f32_up(hi[k] + b.pad);
+                    il[k] = f32_up(lo[k] + b.pad); ih[k] = f32_down(hi[k] - b.pad);
+                    inner_ok = inner_ok && il[k] <= ih[k];
+                }
+                ef[4 * i] = make_float4(ol[0], ol[1], ol[2], 0.f);
+                ef[4 * i + 1] = make_float4(oh[0], oh[1], oh[2], 0.f);
+                if (inner_ok) {  // else: stays NaN, the certain-hit test never passes
+                    ef[4 * i + 2] = make_float4(il[0], il[1], il[2], 0.f);
+                    ef[4 * i + 3] = make_float4(ih[0], ih[1], ih[2], 0.f);
+                }
+            }
+        }
+        if ((rc = upload(s, ef, &s->d.elemf))) return bail(rc);
+    }
     std::vector<DMaterial> mats(desc->num_materials);
     for (uint32_t i = 0; i < desc->num_materials; i++) {
         const hnm_material& m = desc->materials[i];

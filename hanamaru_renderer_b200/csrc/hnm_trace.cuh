@@ -1,23 +1,23 @@
-// hnm_trace.cuh -- the closest-hit kernel: persistent warps, while-while traversal, dynamic ray fetch,
-// f32 traversal with exact f64 confirmation.
-//
-// One launch serves up to two ray lists ("jobs"): the camera-path rays of bounce b and the NEE shadow rays of
-// bounce b-1 (both are closest-hit queries in the reference: src/renderer.rs:176,280).  Each lane owns one ray.
+// hnm_trace.cuh -- closest hit in two kernels: k_trace (f32 candidate search) and k_confirm (exact f64 tests).
 //
 // What decides a result is ONLY the reference's f64 primitive arithmetic (hnm_device.cuh: tri_test, sphere_test,
-// cuboid_test); everything that merely decides WHICH primitives get that test runs in f32 and is conservative:
+// cuboid_test).  Everything that merely decides WHICH primitives get that test is conservative f32 work:
 //   * node boxes: f32, rounded outward and padded (hnm_scene.cuh);
-//   * triangles: a Moeller-Trumbore pre-test in f32 with running error bounds.  A triangle that may be hit at or
-//     before the current bound becomes a CANDIDATE (kept in a 4-entry per-lane list); a triangle that is hit
-//     for certain, by the full error margin, lowers `best_ub`, a safe upper bound of the closest-hit distance
-//     that culls nodes and later candidates.  The exact f64 test runs on the surviving candidates when the ray
-//     retires -- a warp-converged point, so the expensive f64 code executes with most lanes active -- or
-//     earlier if a lane's list overflows.  ncu, round 1: 29.5 exact triangle tests per ray made FP64 the
-//     busiest pipe at 5-18 of 32 lanes per instruction.
-//   * spheres / cuboids (a handful per scene) are tested exactly on the spot.
-// A warp keeps traversing until fewer than TRACE_REFILL lanes still have work; then finished lanes confirm
-// their candidates, write their hits, push the hit's queue class (miss / delta BSDF / NEE BSDF; one atomic per
-// warp and class) and pull new rays from a global work counter.
+//   * triangles: a Moeller-Trumbore pre-test in f32 with running error bounds; spheres and cuboids: f32 versions of
+//     their own tests with error bounds.  A primitive that may be hit at or before the current bound becomes a
+//     CANDIDATE of its ray (a list of up to TRACE_CAND entries in global memory); a primitive that is hit for
+//     certain, by the full error margin, lowers `best_ub`, a safe upper bound of the closest-hit distance that
+//     culls nodes and later candidates.
+// k_trace: persistent warps, dynamic ray fetch, majority-vote scheduled traversal.  It holds no f64 state at all
+// (ncu, round 1: with the exact tests and the f64 ray inside this kernel it needed 96-110 registers, 5 CTAs/SM,
+// and 4 -> 5 CTAs/SM alone was worth 17 %).  It writes per ray: the candidate list, its length (or a flag) and
+// the final bound.
+// k_confirm: one thread per ray, coalesced: the exact f64 test on the candidates whose lower bound does not
+// exceed the final bound -> the closest hit (ties resolved by the reference's DFS order, see tri_test), written
+// as the hit record; camera-path hits are classified into the miss / delta-BSDF / NEE-BSDF shading queues.  A ray
+// whose list overflowed is traced again here by the plain exact traversal (hnm_device.cuh: trace()).
+// One launch of each serves up to two ray lists ("jobs"): the camera-path rays of bounce b and the NEE shadow rays
+// of bounce b-1 (both are closest-hit queries in the reference: src/renderer.rs:176,280).
 #ifndef HNM_TRACE_CUH
 #define HNM_TRACE_CUH
 
@@ -26,13 +26,10 @@
 namespace hnm {
 
 #ifndef HNM_TRACE_MIN_BLOCKS
-#define HNM_TRACE_MIN_BLOCKS 5  /* 96 registers: measured best of 4 (108 regs) / 5 / 6 (80 regs, spills) */
+#define HNM_TRACE_MIN_BLOCKS 8  /* 64 registers */
 #endif
 #ifndef HNM_TRACE_REFILL
 #define HNM_TRACE_REFILL 20
-#endif
-#ifndef HNM_TRACE_TOPREG
-#define HNM_TRACE_TOPREG 0      /* keep the stack top in a register */
 #endif
 #ifndef HNM_TRACE_NODE_STEPS
 #define HNM_TRACE_NODE_STEPS 3  /* max node steps per scheduling vote */
@@ -44,17 +41,32 @@ namespace hnm {
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_REFILL = HNM_TRACE_REFILL;  // refetch when fewer lanes than this are still traversing
 
+constexpr int TRACE_CAND = 8;                    // candidate-list capacity per ray
+constexpr uint32_t CAND_OVERFLOW = 0xFFFFFFFFu;  // list overflowed: k_confirm runs the exact traversal
+constexpr uint32_t CAND_OCCLUDED = 0xFFFFFFFEu;  // bounded query ended early: report "no hit"
+// candidate id: kind (LEAF_TRI / LEAF_SPHERE / LEAF_CUBOID) << 30 | triangle index (reference leaf order) or element id
+
 struct TraceJob {
     const double* ray[6];  // origin xyz, direction xyz (SoA)
-    double* hit_t; double* hit_u; double* hit_v; uint2* hit_id;
     const uint32_t* count;     // rays in this list (device memory)
     const float* tmax;         // optional: bounded query, see k_trace (null = closest hit along the whole ray)
+    uint32_t slot0;            // candidate-list slot of this job's ray 0
+    // written by k_confirm
+    double* hit_t; double* hit_u; double* hit_v; uint2* hit_id;
     // classification of camera-path hits into shading queues (null for shadow rays)
     uint32_t* cnt_miss; uint32_t* cnt_delta; uint32_t* cnt_nee;
     uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee;
 };
+struct CandLists {
+    uint32_t* id;   // [TRACE_CAND][stride]
+    float* lo;      // [TRACE_CAND][stride] lower bound of the candidate's distance
+    uint32_t* n;    // [stride] entries, or CAND_OVERFLOW / CAND_OCCLUDED
+    float* ub;      // [stride] final upper bound of the closest-hit distance
+    uint32_t stride;
+};
 struct TraceArgs {
     TraceJob job[2];
+    CandLists cand;
     uint32_t* work;                 // global fetch counter, zero at launch
     unsigned long long* stats;      // S_* counters
     int njobs;
@@ -123,6 +135,69 @@ HNM_D bool tri_pretest(const float4* __restrict__ tf, const RayF& R, float& best
     return true;
 }
 
+// Conservative f32 version of Cuboid::intersect's slab test (src/scene.rs:152-183 via src/bvh.rs:20-39).
+// ef[0], ef[1] = the box rounded OUTWARD and padded, ef[2], ef[3] = rounded INWARD and shrunk by the same pad.
+// Returns false only if the exact test cannot hit at a distance <= best_ub; *t_lo = lower bound of that distance.
+// Lowers best_ub when the ray passes through the inner box for certain.
+HNM_D bool cuboid_pretest(const float4* __restrict__ ef, const RayF& R, float& best_ub, float* t_lo) {
+    const float W = 4.76837158203125e-07f;  // 2^-21
+    const float4 lo = __ldg(ef), hi = __ldg(ef + 1);
+    float a0 = (lo.x - R.ox) * R.ix, b0 = (hi.x - R.ox) * R.ix;
+    float a1 = (lo.y - R.oy) * R.iy, b1 = (hi.y - R.oy) * R.iy;
+    float a2 = (lo.z - R.oz) * R.iz, b2 = (hi.z - R.oz) * R.iz;
+    float tmin = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+    float tmax = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+    const float out_lo = tmin - fabsf(tmin) * W, out_up = tmax + fabsf(tmax) * W;
+    // distances are measured from the (possibly advanced) f32 origin: the true t is larger by t0 >= 0
+    if (!((out_lo <= out_up) && (out_up >= -R.t0) && (out_lo <= best_ub))) return false;
+    *t_lo = out_lo;
+    if (R.t0 == 0.0f) {
+        const float4 li = __ldg(ef + 2), hj = __ldg(ef + 3);
+        a0 = (li.x - R.ox) * R.ix; b0 = (hj.x - R.ox) * R.ix;
+        a1 = (li.y - R.oy) * R.iy; b1 = (hj.y - R.oy) * R.iy;
+        a2 = (li.z - R.oz) * R.iz; b2 = (hj.z - R.oz) * R.iz;
+        tmin = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+        tmax = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+        const float in_lo = tmin + fabsf(tmin) * W, in_up = tmax - fabsf(tmax) * W;
+        // (li <= hj componentwise is the host's job: a degenerate inner box is stored as NaN and never passes)
+        if (in_lo <= in_up && in_up > 0.0f) {
+            // the ray crosses the inner box, so the exact test hits.  Its distance is tmin if tmin >= 0 (entry into the
+            // true box, not later than the entry into the inner box), else tmax (<= out_up).
+            const float t_ub = out_lo > 0.0f ? in_lo : out_up;
+            best_ub = fminf(best_ub, t_ub);
+        }
+    }
+    return true;
+}
+
+// Conservative f32 version of Sphere::intersect (src/scene.rs:58-78): t = -b - sqrt(b^2 - c), hit iff d > 0 && t > 0.
+// ef[0] = (centre, radius).  Same contract as cuboid_pretest.
+HNM_D bool sphere_pretest(const float4* __restrict__ ef, const RayF& R, float& best_ub, float* t_lo) {
+    const float E = 9.5367431640625e-07f;  // 2^-20: a generous bound for a handful of f32 roundings
+    const float4 c = __ldg(ef);
+    const float ax = R.ox - c.x, ay = R.oy - c.y, az = R.oz - c.z;  // each within R.K of the exact difference
+    const float dx = -R.rx, dy = -R.ry, dz = -R.rz;
+    const float A1 = l1(ax, ay, az);
+    const float b = ax * dx + ay * dy + az * dz;
+    const float Eb = 2.0f * R.K + A1 * E;                           // |d|_1 <= sqrt(3) < 2
+    const float aa = ax * ax + ay * ay + az * az;
+    const float rr = c.w * c.w;
+    const float cc = aa - rr;
+    const float Ec = 2.0f * A1 * R.K + 3.0f * R.K * R.K + (aa + rr) * E;
+    const float disc = b * b - cc;
+    const float Ed = 2.0f * fabsf(b) * Eb + Eb * Eb + Ec + (b * b + fabsf(cc)) * E;
+    if (!(disc + Ed > 0.0f)) return false;                          // d <= 0 for certain
+    const float s_hi = sqrtf(disc + Ed) * 1.000001f;
+    const float s_lo = disc - Ed > 0.0f ? sqrtf(disc - Ed) * 0.999999f : 0.0f;
+    const float Er = (fabsf(b) + s_hi) * E;                         // roundings of the two subtractions below
+    const float tl = ((-b - Eb) - s_hi) - Er, th = ((-b + Eb) - s_lo) + Er;  // tl <= t <= th (from the f32 origin)
+    if (!(th > -R.t0)) return false;                                // t <= 0 for certain
+    if (tl > best_ub) return false;
+    *t_lo = tl;
+    if (disc - Ed > 0.0f && tl > 0.0f && R.t0 == 0.0f) best_ub = fminf(best_ub, th * 1.000001f + 1e-30f);
+    return true;
+}
+
 // `cur` of a lane without a ray: a LEAF_NONE link, so that "holds a node" is cur >= 0 and "holds a leaf" is
 // cur < 0 && cur != TRACE_IDLE -- two ballots per scheduling round instead of three
 constexpr int32_t TRACE_IDLE = ~(int32_t)((uint32_t)LEAF_NONE << 29);
@@ -135,128 +210,65 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     const uint32_t ntot = n0 + n1;
     const float W = 4.76837158203125e-07f;  // 2^-21, see hnm_device.cuh: trace()
 
-    // traversal stack: the top entry lives in a register (`top`), the rest in local memory -- a pop hands `top` to
-    // `cur` at once and the reload of the next entry is off the critical path (ncu, round 1: the dependent local load
-    // `cur = stack[--sp]` in front of the node fetch was the most-sampled line of the kernel)
     int32_t stack[HNM_STACK];
-    int sp = 0;          // entries on the stack INCLUDING `top`
-    int32_t top = 0;
+    int sp = 0;
     int32_t cur = TRACE_IDLE;
-    bool pending = false;
-    uint32_t idx = 0;
-    D3 o = splat(0.0), dir = splat(0.0);
+    uint32_t slot = 0;       // this ray's candidate list
     RayF R;
     R.ox = R.oy = R.oz = R.ix = R.iy = R.iz = R.rx = R.ry = R.rz = 0.f; R.K = 0.f; R.t0 = 0.f;
-    double t0 = 0.0;
     float best_ub = 3.0e38f;
     float t_occ = -3.0e38f;  // shadow rays: a certain hit closer than this ends the ray (see TraceJob::tmax)
-    Hit best;
-    best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
-    // candidate triangles awaiting the exact test (newest first)
-    uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-    float l0 = 0.f, l1_ = 0.f, l2 = 0.f, l3 = 0.f;
-    int ncand = 0;
-    uint32_t n_nodes = 0, n_prims = 0;
+    uint32_t ncand = 0;
+    uint32_t n_nodes = 0;
     bool more = true;  // warp-uniform: the work counter has not run past the end yet
     uint32_t lk = 0;   // next primitive of the leaf this lane holds
 
-#define HNM_EXACT(g)                                               \
+    // the ray is finished: publish the list header (divergent, but two 4-byte stores)
+#define HNM_FINISH(count_or_flag)                                  \
     {                                                              \
-        DTri tr_ = load_tri(sc.tris + (g));                        \
-        if (STATS) n_prims++;                                      \
-        tri_test(tr_, (g), o, dir, best);                          \
+        __stcs(A.cand.n + slot, (uint32_t)(count_or_flag));        \
+        __stcs(A.cand.ub + slot, best_ub);                         \
+        cur = TRACE_IDLE;                                          \
     }
-#if HNM_TRACE_TOPREG
 #define HNM_POP()                                                  \
     {                                                              \
-        if (sp == 0) { cur = TRACE_IDLE; pending = true; }         \
-        else {                                                     \
-            cur = top;                                             \
-            sp--;                                                  \
-            if (sp > 0) top = stack[sp - 1];                       \
-        }                                                          \
-    }
-#define HNM_PUSH(v)                                                \
-    {                                                              \
-        if (sp > 0) stack[sp - 1] = top;                           \
-        top = (v);                                                 \
-        sp++;                                                      \
-    }
-#else
-#define HNM_POP()                                                  \
-    {                                                              \
-        if (sp == 0) { cur = TRACE_IDLE; pending = true; }         \
+        if (sp == 0) HNM_FINISH(ncand)                             \
         else cur = stack[--sp];                                    \
     }
-#define HNM_PUSH(v) { stack[sp++] = (v); }
-#endif
 
     for (;;) {
-        // ---- converged: confirm candidates of finished rays in f64, retire them ----------------------------
-        {
-            int cls = -1;
-            if (pending) {
-                // the exact closest hit is among the candidates whose lower bound does not exceed the bound
-                if (ncand > 0 && l0 <= best_ub) HNM_EXACT(c0)
-                if (ncand > 1 && l1_ <= best_ub) HNM_EXACT(c1)
-                if (ncand > 2 && l2 <= best_ub) HNM_EXACT(c2)
-                if (ncand > 3 && l3 <= best_ub) HNM_EXACT(c3)
-                if (ncand < 0) { best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0; }  // occluded shadow ray
-                ncand = 0;
-                const bool j1 = idx >= n0;
-                const TraceJob& J = A.job[j1 ? 1 : 0];
-                const uint32_t q = j1 ? idx - n0 : idx;
-                __stcs(J.hit_t + q, best.t); __stcs(J.hit_u + q, best.u); __stcs(J.hit_v + q, best.v);
-                __stcs(J.hit_id + q, make_uint2(best.kind, best.id));
-                if (!j1 && J.q_miss) {
-                    if (best.kind == LEAF_NONE) cls = 0;
-                    else {
-                        uint32_t el = best.kind == LEAF_TRI ? sc.tri_elem[best.id] : best.id;
-                        int surface = sc.materials[sc.elements[el].material].surface;
-                        cls = nee_available(surface) ? 2 : 1;
-                    }
-                }
-                pending = false;
-            }
-            const TraceJob& J0 = A.job[0];
-            if (J0.q_miss) {
-                warp_queue_push(cls == 0, J0.cnt_miss, J0.q_miss, idx, lane);
-                warp_queue_push(cls == 1, J0.cnt_delta, J0.q_delta, idx, lane);
-                warp_queue_push(cls == 2, J0.cnt_nee, J0.q_nee, idx, lane);
-            }
-        }
         // ---- converged: fetch new rays -----------------------------------------------------------------------
         {
             unsigned need = __ballot_sync(0xFFFFFFFFu, cur == TRACE_IDLE);
             if (need) {
                 int leader = __ffs(need) - 1;
                 uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(A.work, (uint32_t)__popc(need));
+                if (more && lane == leader) base = atomicAdd(A.work, (uint32_t)__popc(need));
                 base = __shfl_sync(0xFFFFFFFFu, base, leader);
-                more = base + (uint32_t)__popc(need) < ntot;
-                if (cur == TRACE_IDLE) {
-                    idx = base + __popc(need & ((1u << lane) - 1u));
+                if (more && cur == TRACE_IDLE) {
+                    const uint32_t idx = base + __popc(need & ((1u << lane) - 1u));
                     if (idx < ntot) {
                         const bool j1 = idx >= n0;
                         const TraceJob& J = A.job[j1 ? 1 : 0];
                         const uint32_t q = j1 ? idx - n0 : idx;
-                        // streaming (evict-first) loads and stores for the ray / hit records: the L1 is for the tree
-                        o = d3(__ldcs(J.ray[0] + q), __ldcs(J.ray[1] + q), __ldcs(J.ray[2] + q));
-                        dir = d3(__ldcs(J.ray[3] + q), __ldcs(J.ray[4] + q), __ldcs(J.ray[5] + q));
-                        best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
+                        slot = J.slot0 + q;
+                        // streaming (evict-first) loads and stores for the ray / list records: the L1 is for the tree
+                        const D3 o = d3(__ldcs(J.ray[0] + q), __ldcs(J.ray[1] + q), __ldcs(J.ray[2] + q));
+                        const D3 dir = d3(__ldcs(J.ray[3] + q), __ldcs(J.ray[4] + q), __ldcs(J.ray[5] + q));
                         best_ub = 3.0e38f;
                         t_occ = -3.0e38f;
                         ncand = 0;
-                        t0 = 0.0;
+                        double t0 = 0.0;
                         sp = 0;
                         cur = 0;
                         lk = 0;
                         float fmaxo = fmaxf(fmaxf(fabsf((float)o.x), fabsf((float)o.y)), fabsf((float)o.z));
                         if (fmaxo > sc.far_limit) {
+                            // the f32 origin would lose too many bits: advance it to the scene box first
                             double dist;
                             bool h = aabb_intersect_ray(sc.bounds_lo[0], sc.bounds_lo[1], sc.bounds_lo[2], sc.bounds_hi[0], sc.bounds_hi[1],
                                                         sc.bounds_hi[2], o, dir, &dist);
-                            if (!h) { cur = TRACE_IDLE; pending = true; }
+                            if (!h) HNM_FINISH(0u)  // cannot hit anything: every primitive lies inside the scene box
                             else if (dist > 0.0 && dist < sc.inf) t0 = dist * (1.0 - 1e-6);
                         } else if (J.tmax) {
                             // Bounded query (NEE shadow rays): the caller only looks at the closest hit if it lies within
@@ -275,20 +287,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         R.K = (fmaxf(fmaxf(fabsf(R.ox), fabsf(R.oy)), fabsf(R.oz)) + sc.scene_r) * 4.76837158203125e-07f;
                     }
                 }
+                more = more && base + (uint32_t)__popc(need) < ntot;
             }
-            if (__ballot_sync(0xFFFFFFFFu, cur != TRACE_IDLE || pending) == 0) break;
+            if (__ballot_sync(0xFFFFFFFFu, cur != TRACE_IDLE) == 0) break;
         }
-        // ---- traverse (f32) until too few lanes are left -----------------------------------------------------
-        // Majority-vote scheduling.  Each iteration every lane is in one of two states: it holds a NODE (cur >= 0)
-        // or a LEAF with triangles left (cur < 0).  The warp executes ONE step of whichever kind the majority of
-        // lanes needs -- a node step (two f32 slab tests) or a leaf step (one f32 triangle pre-test) -- and the
-        // minority idles until it becomes the majority.  The loop is warp-uniform (full-mask ballots): with
-        // independent thread scheduling a per-lane `while (has_ray)` never reconverges, and a strict while-while
-        // loop (all lanes descend to a leaf, then all test it) ran at 4 of 32 lanes per instruction on the
-        // incoherent bounces because the longest descent of the warp sets the pace (ncu, round 1).
+        // ---- traverse until too few lanes are left -----------------------------------------------------------
+        // Majority-vote scheduling.  Every lane is in one of two states: it holds a NODE (cur >= 0) or a LEAF with
+        // primitives left (cur < 0).  The warp executes a short phase of whichever kind the majority of lanes needs
+        // -- node steps (two f32 slab tests each) or leaf steps (one f32 pre-test each) -- and the minority idles
+        // until it becomes the majority.  The loop is warp-uniform (full-mask ballots): with independent thread
+        // scheduling a per-lane `while (has_ray)` never reconverges, and a strict while-while loop (all lanes
+        // descend to a leaf, then all test it) ran at 4 of 32 lanes per instruction on the incoherent bounces
+        // because the longest descent of the warp sets the pace (ncu, round 1).
         for (;;) {
-            const bool is_node = cur >= 0;
-            const unsigned nm = __ballot_sync(0xFFFFFFFFu, is_node);
+            const unsigned nm = __ballot_sync(0xFFFFFFFFu, cur >= 0);
             const unsigned lm = __ballot_sync(0xFFFFFFFFu, cur < 0 && cur != TRACE_IDLE);
             const int nn = __popc(nm), nl = __popc(lm);
             if (nn + nl == 0 || (more && nn + nl < TRACE_REFILL)) break;  // too few lanes left: refill (lanes keep their state)
@@ -319,9 +331,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         const bool swap = lo1 < lo0;
                         lk = 0;
                         if (h0 || h1) {
-                            // near child next; the far one (if both are hit) becomes the new stack top
+                            // near child next; the far one (if both are hit) goes on the stack
                             cur = (h0 && !(h1 && swap)) ? m3.x : m3.y;
-                            if (h0 && h1 && sp < HNM_STACK) HNM_PUSH(swap ? m3.x : m3.y)
+                            if (h0 && h1 && sp < HNM_STACK) stack[sp++] = swap ? m3.x : m3.y;
                         } else {
                             HNM_POP()
                         }
@@ -329,61 +341,127 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                 }
             } else {
 #pragma unroll
-              for (int rep = 0; rep < HNM_TRACE_LEAF_STEPS; rep++) {
-                if (cur < 0 && cur != TRACE_IDLE) {
-                // one primitive of the leaf this lane holds
-                const int kind = leaf_kind(cur);
-                const uint32_t first = leaf_first(cur);
-                bool leaf_done = true;
-                if (kind == LEAF_TRI) {
-                    float tlo;
-                    const uint32_t pos = first + lk;
-                    if (tri_pretest(sc.trif + 3 * (size_t)pos, R, best_ub, &tlo)) {
-                        const uint32_t g = __ldg(sc.tri_perm + pos);  // index in the reference's leaf order (ties)
-                        if (ncand == 4) {
-                            // list full: the oldest entry either drops out (bound moved below it) or is confirmed now
-                            if (l3 <= best_ub) {
-                                HNM_EXACT(c3)
-                                best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
-                            }
-                            ncand = 3;
+                for (int rep = 0; rep < HNM_TRACE_LEAF_STEPS; rep++) {
+                    if (cur < 0 && cur != TRACE_IDLE) {
+                        // one primitive of the leaf this lane holds
+                        const int kind = leaf_kind(cur);
+                        const uint32_t first = leaf_first(cur);
+                        bool leaf_done = true, cand = false;
+                        uint32_t cid = 0;
+                        float tlo = 0.f;
+                        if (kind == LEAF_TRI) {
+                            const uint32_t pos = first + lk;
+                            cand = tri_pretest(sc.trif + 3 * (size_t)pos, R, best_ub, &tlo);
+                            if (cand) cid = __ldg(sc.tri_perm + pos);  // index in the reference's leaf order (ties)
+                            lk++;
+                            leaf_done = lk >= leaf_count(cur);
+                        } else if (kind == LEAF_SPHERE) {
+                            cand = sphere_pretest(sc.elemf + 4 * (size_t)first, R, best_ub, &tlo);
+                            cid = ((uint32_t)LEAF_SPHERE << 30) | first;
+                        } else if (kind == LEAF_CUBOID) {
+                            cand = cuboid_pretest(sc.elemf + 4 * (size_t)first, R, best_ub, &tlo);
+                            cid = ((uint32_t)LEAF_CUBOID << 30) | first;
                         }
-                        c3 = c2; l3 = l2; c2 = c1; l2 = l1_; c1 = c0; l1_ = l0;
-                        c0 = g; l0 = tlo;
-                        ncand++;
+                        if (cand) {
+                            if (ncand < (uint32_t)TRACE_CAND) {
+                                const size_t at = (size_t)ncand * A.cand.stride + slot;
+                                __stcs(A.cand.id + at, cid);
+                                __stcs(A.cand.lo + at, tlo);
+                                ncand++;
+                            } else {
+                                ncand = CAND_OVERFLOW;  // k_confirm traces this ray exactly
+                            }
+                        }
+                        if (ncand == CAND_OVERFLOW) {
+                            HNM_FINISH(CAND_OVERFLOW)
+                        } else if (best_ub < t_occ) {
+                            // bounded query: something certainly lies in front of the point the caller asked about
+                            HNM_FINISH(CAND_OCCLUDED)
+                        } else if (leaf_done) {
+                            lk = 0;
+                            HNM_POP()
+                        }
                     }
-                    lk++;
-                    leaf_done = lk >= leaf_count(cur);
-                } else if (kind == LEAF_SPHERE) {
-                    if (STATS) n_prims++;
-                    sphere_test(sc.elements[first], first, sc.elements, o, dir, best);
-                    best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
-                } else if (kind == LEAF_CUBOID) {
-                    if (STATS) n_prims++;
-                    cuboid_test(sc.elements[first], first, sc.elements, o, dir, best);
-                    best_ub = fminf(best_ub, __double2float_ru(best.t - t0));
                 }
-                if (best_ub < t_occ) {
-                    // bounded query: something certainly lies in front of the point the caller asked about
-                    ncand = -1;
-                    cur = TRACE_IDLE;
-                    pending = true;
-                } else if (leaf_done) {
-                    lk = 0;
-                    HNM_POP()
-                }
-                }
-              }
             }
         }
     }
-#undef HNM_EXACT
+#undef HNM_FINISH
 #undef HNM_POP
-#undef HNM_PUSH
     if (blockIdx.x == 0 && threadIdx.x == 0 && A.stat_segments >= 0) atomicAdd(&A.stats[A.stat_segments], (unsigned long long)n0);
     if (STATS) {
-        for (int s = 16; s > 0; s >>= 1) { n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, s); n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, s); }
-        if (lane == 0) { atomicAdd(&A.stats[A.stat_nodes], (unsigned long long)n_nodes); atomicAdd(&A.stats[A.stat_prims], (unsigned long long)n_prims); }
+        for (int s = 16; s > 0; s >>= 1) n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, s);
+        if (lane == 0) atomicAdd(&A.stats[A.stat_nodes], (unsigned long long)n_nodes);
+    }
+}
+
+// Exact closest hit of every ray from its candidate list; hit records; shading queues for job 0.
+template <bool STATS>
+__global__ void __launch_bounds__(256) k_confirm(DScene sc, TraceArgs A) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n0 = *A.job[0].count;
+    const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
+    const uint32_t ntot = n0 + n1;
+    const uint32_t n_round = (ntot + 31u) & ~31u;  // warp-uniform trip count: the queue pushes ballot
+    uint32_t n_prims = 0;
+    const bool classify = A.job[0].q_miss != nullptr;
+    for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
+        int cls = -1;
+        if (idx < ntot) {
+            const bool j1 = idx >= n0;
+            const TraceJob& J = A.job[j1 ? 1 : 0];
+            const uint32_t q = j1 ? idx - n0 : idx;
+            const uint32_t slot = J.slot0 + q;
+            const uint32_t n = __ldcs(A.cand.n + slot);
+            Hit best;
+            best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
+            if (n != 0u && n != CAND_OCCLUDED) {
+                const D3 o = d3(J.ray[0][q], J.ray[1][q], J.ray[2][q]);
+                const D3 dir = d3(J.ray[3][q], J.ray[4][q], J.ray[5][q]);
+                if (n == CAND_OVERFLOW) {
+                    TraceStats st{0, 0};
+                    best = trace<STATS>(sc, o, dir, &st);
+                    if (STATS) n_prims += st.prims;
+                } else {
+                    const float ub = __ldcs(A.cand.ub + slot);
+                    for (uint32_t k = 0; k < n; k++) {
+                        const size_t at = (size_t)k * A.cand.stride + slot;
+                        if (__ldcs(A.cand.lo + at) > ub) continue;  // culled after it was listed
+                        const uint32_t cid = __ldcs(A.cand.id + at);
+                        const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
+                        if (STATS) n_prims++;
+                        if (kind == LEAF_TRI) {
+                            DTri tr = load_tri(sc.tris + id);
+                            tri_test(tr, id, o, dir, best);
+                        } else if (kind == LEAF_SPHERE) {
+                            sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
+                        } else {
+                            cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
+                        }
+                    }
+                }
+            }
+            __stcs(J.hit_t + q, best.t); __stcs(J.hit_u + q, best.u); __stcs(J.hit_v + q, best.v);
+            __stcs(J.hit_id + q, make_uint2(best.kind, best.id));
+            if (!j1 && classify) {
+                if (best.kind == LEAF_NONE) cls = 0;
+                else {
+                    uint32_t el = best.kind == LEAF_TRI ? sc.tri_elem[best.id] : best.id;
+                    int surface = sc.materials[sc.elements[el].material].surface;
+                    cls = nee_available(surface) ? 2 : 1;
+                }
+            }
+        }
+        if (classify) {
+            const TraceJob& J0 = A.job[0];
+            warp_queue_push(cls == 0, J0.cnt_miss, J0.q_miss, idx, lane);
+            warp_queue_push(cls == 1, J0.cnt_delta, J0.q_delta, idx, lane);
+            warp_queue_push(cls == 2, J0.cnt_nee, J0.q_nee, idx, lane);
+        }
+    }
+    if (STATS) {
+        for (int s = 16; s > 0; s >>= 1) n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, s);
+        if (lane == 0) atomicAdd(&A.stats[A.stat_prims], (unsigned long long)n_prims);
     }
 }
 
