@@ -139,8 +139,8 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
 #define MEM(i) mem[(i) * T]
     uint64_t a, b, c, d, e, f, g, h;
     a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) { ISAAC_MIX(a, b, c, d, e, f, g, h) }
+#pragma unroll
+    for (int i = 0; i < 4; i++) { ISAAC_MIX(a, b, c, d, e, f, g, h) }  // constants: folded at compile time
     // first pass mixes in rsl = [s0 s1 s2 s3 0 0 ...]
     a += s0; b += s1; c += s2; d += s3;
 #pragma unroll 1
@@ -159,15 +159,27 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
         MEM(i + 4) = e; MEM(i + 5) = f; MEM(i + 6) = g; MEM(i + 7) = h;
     }
     // isaac64(): a = 0, b = 0, c = 1  ->  aa = 0, bb = 1
+    // One step:  x = mem[i];  aa = mix(aa) + mem[i ^ 128];  y = mem[ind(x)] + aa + bb;  mem[i] = y;
+    //            bb = mem[ind(y >> 8)] + x;  rsl[i] = bb.
+    // Written naively, the data-dependent load mem[ind(x)] of step i+1 must wait for the store mem[i] = y of step i
+    // (it may alias), and y waits for bb, which waits for the other data-dependent load: two shared-memory
+    // latencies per step on the critical chain.  Here x and mem[ind(x)] of the NEXT step are loaded before this
+    // step's store and the one possible alias (ind(x') == i) is patched by forwarding y: one latency per step.
     uint64_t aa = 0, bb = 1;
-#define ISAAC_STEP(mixexpr, i, i2, SINK)                         \
-    {                                                           \
-        uint64_t x = MEM(i);                                    \
-        aa = (mixexpr) + MEM(i2);                               \
-        uint64_t y = MEM(((uint32_t)x >> 3) & 255u) + aa + bb;  \
-        MEM(i) = y;                                             \
-        bb = MEM(((uint32_t)y >> 11) & 255u) + x;               \
-        SINK(i, bb);                                            \
+    uint64_t xn = MEM(0);
+    uint64_t pn = MEM(((uint32_t)xn >> 3) & 255u);
+#define ISAAC_STEP(mixexpr, i, i2, SINK)                             \
+    {                                                               \
+        const uint64_t x = xn, p = pn;                              \
+        xn = MEM(((i) + 1) & 255);  /* i == 255: a dummy load */    \
+        const uint32_t jn = ((uint32_t)xn >> 3) & 255u;             \
+        pn = MEM(jn);                                               \
+        aa = (mixexpr) + MEM(i2);                                   \
+        const uint64_t y = p + aa + bb;                             \
+        MEM(i) = y;                                                 \
+        if (jn == (uint32_t)(i)) pn = y;                            \
+        bb = MEM(((uint32_t)y >> 11) & 255u) + x;                   \
+        SINK(i, bb);                                                \
     }
 #define ISAAC_NOSINK(i, v)
     // only the last KEEP outputs (rsl[256-KEEP .. 255], the first KEEP words of the stream) are handed to `sink`
