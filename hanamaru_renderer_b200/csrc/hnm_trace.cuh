@@ -38,6 +38,9 @@ namespace hnm {
 #define HNM_TRACE_LEAF_STEPS 2  /* max leaf steps per scheduling vote */
 #endif
 
+#ifndef HNM_CONFIRM_MIN_BLOCKS
+#define HNM_CONFIRM_MIN_BLOCKS 3
+#endif
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_REFILL = HNM_TRACE_REFILL;  // refetch when fewer lanes than this are still traversing
 
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
 
 // Exact closest hit of every ray from its candidate list; hit records; shading queues for job 0.
 template <bool STATS>
-__global__ void __launch_bounds__(256) k_confirm(DScene sc, TraceArgs A) {
+__global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene sc, TraceArgs A) {
     const int lane = threadIdx.x & 31;
     const uint32_t n0 = *A.job[0].count;
     const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
@@ -412,32 +415,36 @@ __global__ void __launch_bounds__(256) k_confirm(DScene sc, TraceArgs A) {
             const TraceJob& J = A.job[j1 ? 1 : 0];
             const uint32_t q = j1 ? idx - n0 : idx;
             const uint32_t slot = J.slot0 + q;
+            // everything that does not depend on the list is requested up front: the kernel is a chain of dependent
+            // loads (header -> entries -> triangle) and latency is all it costs (ncu, round 1: 15 long-scoreboard
+            // stall cycles per issued instruction)
             const uint32_t n = __ldcs(A.cand.n + slot);
+            const float ub = __ldcs(A.cand.ub + slot);
+            const uint32_t cid0 = __ldcs(A.cand.id + slot);   // entry 0 (unspecified if n == 0, always readable)
+            const float lo0 = __ldcs(A.cand.lo + slot);
+            const D3 o = d3(__ldcs(J.ray[0] + q), __ldcs(J.ray[1] + q), __ldcs(J.ray[2] + q));
+            const D3 dir = d3(__ldcs(J.ray[3] + q), __ldcs(J.ray[4] + q), __ldcs(J.ray[5] + q));
             Hit best;
             best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
-            if (n != 0u && n != CAND_OCCLUDED) {
-                const D3 o = d3(J.ray[0][q], J.ray[1][q], J.ray[2][q]);
-                const D3 dir = d3(J.ray[3][q], J.ray[4][q], J.ray[5][q]);
-                if (n == CAND_OVERFLOW) {
-                    TraceStats st{0, 0};
-                    best = trace<STATS>(sc, o, dir, &st);
-                    if (STATS) n_prims += st.prims;
-                } else {
-                    const float ub = __ldcs(A.cand.ub + slot);
-                    for (uint32_t k = 0; k < n; k++) {
-                        const size_t at = (size_t)k * A.cand.stride + slot;
-                        if (__ldcs(A.cand.lo + at) > ub) continue;  // culled after it was listed
-                        const uint32_t cid = __ldcs(A.cand.id + at);
-                        const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
-                        if (STATS) n_prims++;
-                        if (kind == LEAF_TRI) {
-                            DTri tr = load_tri(sc.tris + id);
-                            tri_test(tr, id, o, dir, best);
-                        } else if (kind == LEAF_SPHERE) {
-                            sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
-                        } else {
-                            cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
-                        }
+            if (n == CAND_OVERFLOW) {
+                TraceStats st{0, 0};
+                best = trace<STATS>(sc, o, dir, &st);
+                if (STATS) n_prims += st.prims;
+            } else if (n != CAND_OCCLUDED) {
+                for (uint32_t k = 0; k < n; k++) {
+                    const size_t at = (size_t)k * A.cand.stride + slot;
+                    const float lo = k == 0 ? lo0 : __ldcs(A.cand.lo + at);
+                    if (lo > ub) continue;  // culled after it was listed
+                    const uint32_t cid = k == 0 ? cid0 : __ldcs(A.cand.id + at);
+                    const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
+                    if (STATS) n_prims++;
+                    if (kind == LEAF_TRI) {
+                        DTri tr = load_tri(sc.tris + id);
+                        tri_test(tr, id, o, dir, best);
+                    } else if (kind == LEAF_SPHERE) {
+                        sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
+                    } else {
+                        cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
                     }
                 }
             }
