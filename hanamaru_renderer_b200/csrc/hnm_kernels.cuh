@@ -448,8 +448,11 @@ __global__ void __launch_bounds__(256) k_shade_miss(RParams P, int bounce) {
 // light samples (Sphere::sample_on_surface, src/scene.rs:92-101) become shadow rays for the next k_trace
 // and the radiance update moves to k_nee_resolve, which keeps the reference's order
 // `accumulation += reflectance * nee` BEFORE `accumulation += reflectance * emission`.
+#ifndef HNM_SHADE_MIN_BLOCKS
+#define HNM_SHADE_MIN_BLOCKS 4  /* 64 registers (spills to local memory): measured best of 2 / 3 / 4 / 5 / 6 */
+#endif
 template <bool NEE>
-__global__ void __launch_bounds__(256) k_shade_surf(RParams P, int bounce) {
+__global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParams P, int bounce) {
     const int cls = NEE ? C_NEE : C_DELTA;
     const uint32_t n = P.counters[bounce * C_STRIDE + cls];
     const uint32_t* queue = NEE ? P.q_nee : P.q_delta;
