@@ -246,13 +246,18 @@ def run_ours(args):
         paths_p = pc["paths"]
         seg, sh = pc["segments"], pc["shadow_rays"]
         nee_events = sh / max(1, scene.desc.contents.num_emissions)
-        # algorithmic bytes per unit (the f64 SoA records actually shipped; DESIGN.md "HBM records"):
-        #   trace    : per ray: read origin+direction 48, write hit (t,u,v 24 + kind/id 8) 32; camera rays also
-        #              write one 4-byte queue entry                                    = 84 B / segment, 80 B / shadow ray
+        # algorithmic HBM bytes per unit (the records actually shipped):
+        #   isaac    : write 32-word tail 256 + first-bounce ray 76 + L 24 + cursor 1                = 357 B / path
+        #   trace    : read origin + direction 48 (+ 4 tmax for shadow rays); write list header 8 + 8 per candidate
+        #              (1.1 candidates per ray measured)                                             = 65 / 69 B per ray
+        #   confirm  : read ray 48 + header 8 + 8 per candidate; write hit 32 (+ 4 queue entry for camera rays);
+        #              the f64 triangles it tests come from the L2-resident scene                    = 101 / 97 B per ray
         #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17; write next ray 76 (survivors; counted
-        #              for all) + event 76 + shadow ray 88                              = 369 B / NEE event
-        #   isaac    : write 32-word tail 256 + ray 76 + L 24 + cursor 1               = 357 B / path
-        per_unit = {"trace": ((84.0 * seg + 80.0 * sh) / max(1, seg + sh), seg + sh), "shade_nee": (369.0, nee_events),
+        #              for all) + event 76 + shadow ray 92                                           = 373 B / NEE event
+        cand = 1.1
+        per_unit = {"trace": ((56.0 + 8 * cand) * seg / max(1, seg + sh) + (60.0 + 8 * cand) * sh / max(1, seg + sh), seg + sh),
+                    "confirm": ((92.0 + 8 * cand) * seg / max(1, seg + sh) + (88.0 + 8 * cand) * sh / max(1, seg + sh), seg + sh),
+                    "shade_nee": (373.0, nee_events),
                     "isaac_raygen": (357.0, paths_p), "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p),
                     "shade_delta": (4 + 48 + 24 + 4 + 32 + 17 + 48 + 76.0, seg - nee_events)}
         if top in per_unit:
@@ -269,7 +274,9 @@ def run_ours(args):
             roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                         "traffic": traffic, "peak_source": peak_src, "launches": nl, "avg_launch_ms": ms / nl,
                         "algorithmic_bytes_per_unit": b, "units_per_launch": units / nl,
-                        "note": "latency/issue bound by design: scene (<= 70 MB) is L2 resident, HBM only carries the wavefront records"}
+                        "note": "not HBM bound by construction: the scene (<= 70 MB) is L2 resident and HBM only carries the wavefront records; "
+                                "ISAAC-64 seeding is ALU-latency bound at 112 paths (224 KB of shared-memory state) per SM, "
+                                "k_trace is issue bound (77 % issue-slot utilisation, profiles/)"}
 
     # ---- end-to-end through the reference-facing call, host buffers, wall clock -----------------------------
     e2e = None

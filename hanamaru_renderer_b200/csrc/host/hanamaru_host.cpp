@@ -500,6 +500,70 @@ std::unique_ptr<BvhScene> BvhScene::from_scene(Scene scene) {
     return bs;
 }
 
+// ---- rand 0.4.3 src/prng/isaac64.rs + src/lib.rs (Rng::next_f64, gen_range) ------------------------------------
+namespace {
+inline void isaac_mix(uint64_t& a, uint64_t& b, uint64_t& c, uint64_t& d, uint64_t& e, uint64_t& f, uint64_t& g, uint64_t& h) {
+    a -= e; f ^= h >> 9;  h += a;
+    b -= f; g ^= a << 9;  a += b;
+    c -= g; h ^= b >> 23; b += c;
+    d -= h; a ^= c << 15; c += d;
+    e -= a; b ^= d >> 14; d += e;
+    f -= b; c ^= e << 20; e += f;
+    g -= c; d ^= f >> 17; f += g;
+    h -= d; e ^= g << 14; g += h;
+}
+}  // namespace
+StdRng::StdRng(const std::vector<uint64_t>& seed) {
+    // from_seed: the seed words, zero padded, become rsl; a = b = c = 0; init(true)
+    for (int i = 0; i < 256; i++) rsl_[i] = i < (int)seed.size() ? seed[i] : 0;
+    uint64_t a, b, c, d, e, f, g, h;
+    a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
+    for (int i = 0; i < 4; i++) isaac_mix(a, b, c, d, e, f, g, h);
+    for (int pass = 0; pass < 2; pass++) {
+        const uint64_t* src = pass == 0 ? rsl_ : mem_;
+        for (int i = 0; i < 256; i += 8) {
+            a += src[i]; b += src[i + 1]; c += src[i + 2]; d += src[i + 3];
+            e += src[i + 4]; f += src[i + 5]; g += src[i + 6]; h += src[i + 7];
+            isaac_mix(a, b, c, d, e, f, g, h);
+            mem_[i] = a; mem_[i + 1] = b; mem_[i + 2] = c; mem_[i + 3] = d;
+            mem_[i + 4] = e; mem_[i + 5] = f; mem_[i + 6] = g; mem_[i + 7] = h;
+        }
+    }
+    isaac64();
+}
+void StdRng::isaac64() {
+    c_ += 1;
+    uint64_t a = a_, b = b_ + c_;
+    for (int i = 0; i < 256; i++) {
+        uint64_t mixed;
+        switch (i & 3) {
+            case 0: mixed = ~(a ^ (a << 21)); break;
+            case 1: mixed = a ^ (a >> 5); break;
+            case 2: mixed = a ^ (a << 12); break;
+            default: mixed = a ^ (a >> 33); break;
+        }
+        uint64_t x = mem_[i];
+        a = mixed + mem_[(i + 128) & 255];
+        uint64_t y = mem_[(x >> 3) & 255] + a + b;
+        mem_[i] = y;
+        b = mem_[(y >> 11) & 255] + x;
+        rsl_[i] = b;
+    }
+    a_ = a; b_ = b; cnt_ = 256;
+}
+uint64_t StdRng::next_u64() {
+    if (cnt_ == 0) isaac64();
+    cnt_ -= 1;
+    return rsl_[cnt_ & 255];
+}
+double StdRng::next_f64() {
+    uint64_t bits = 0x3FF0000000000000ull | (next_u64() & 0xFFFFFFFFFFFFFull);
+    double v;
+    memcpy(&v, &bits, sizeof(v));
+    return v - 1.0;
+}
+double StdRng::gen_range(double low, double high) { return low + (high - low) * next_f64(); }
+
 // ---- scene authoring (src/main.rs) ---------------------------------------------------------------------
 static Skybox make_skybox(const AssetStore& a, const std::string& dir, Vector3 intensity) {
     Skybox s;
@@ -629,6 +693,133 @@ static SceneAndCamera scene_material_examples(const AssetStore& a, const std::st
 }
 SceneAndCamera init_scene_material_examples(const AssetStore& a) { return scene_material_examples(a, "textures/cube/LancellottiChapel"); }
 
+
+// src/main.rs:252-499.  `sky` lets the tests swap the 2048^2 LancellottiChapel cubemap for the one in the asset pack.
+static const char* MARBLE_DIFFUSE = "textures/2d/MarbleFloorTiles2/TexturesCom_MarbleFloorTiles2_1024_c_diffuse.tiff";
+static const char* MARBLE_ROUGHNESS = "textures/2d/MarbleFloorTiles2/TexturesCom_MarbleFloorTiles2_1024_roughness.png";
+static const char* EARTH = "textures/2d/earth_inverse_2048.jpg";
+static double to_radians(double deg) { return deg * (config::PI / 180.0); }
+static Material diamond_material() { return Material{SurfaceType::Refraction(2.42), Texture::white(), Texture::black(), Texture::black()}; }
+static SceneAndCamera scene_rtcamp5(const AssetStore& a, const std::string& sky) {
+    StdRng rng({870, 2000, 304, 2});
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 2.5, 9.0), Vector3(0.0, 1.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 17.0, LensShape::Circle, 0.15, 8.5);
+    Scene& scene = sc.scene;
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/bunny/bunny_face1000.obj", Matrix44::scale_linear(1.5) * Matrix44::translate(1.2, 0.0, 0.0) * Matrix44::rotate_y(0.2),
+        Material{SurfaceType::Refraction(1.5), Texture::from_color(Color(0.7, 0.7, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.1))})));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/bunny/bunny_face1000_flip.obj", Matrix44::scale(1.5, 1.5, 1.5) * Matrix44::translate(-1.2, 0.0, 0.0) * Matrix44::rotate_y(-0.2),
+        Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 0.04, 0.04)), Texture::black(), Texture::from_color(Color::from_one(0.1))})));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/dia/dia.obj",
+        Matrix44::translate(3.1, 0.0, 0.8) * Matrix44::scale_linear(1.0) * Matrix44::rotate_y(-0.5) * Matrix44::rotate_x(to_radians(40.35)), diamond_material())));
+    scene.add(std::make_unique<Sphere>(Vector3(0.0, 0.5, -0.5), 0.5,
+                                       Material{SurfaceType::GGX(0.8), Texture::white(), Texture::from_image(a.image(EARTH), Color(5.0, 5.0, 2.0)),
+                                                Texture::from_color(Color::from_one(0.05))}));
+    scene.add(std::make_unique<Sphere>(Vector3(-3.5, 0.5, 0.0), 0.5,
+                                       Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 1.0, 1.0)), Texture::black(), tex_path(a, EARTH)}));
+    struct Ball { double x, y, z, r, hue, rough; };
+    const Ball balls[5] = {{0.5018854352719382, 0.3899602675366644, 1.8484239850862165, 0.3899602675366644, 0.2, 0.01},
+                           {-0.5748933256792994, 0.2951263257801348, 2.266298272012876, 0.2951263257801348, 0.4, 0.05},
+                           {-0.9865234498515534, 0.3386858117447873, 2.9809338871934585, 0.3386858117447873, 0.6, 0.02},
+                           {0.6946459502665004, 0.2764689077971783, 2.7455446851003025, 0.2764689077971783, 0.05, 0.0},
+                           {3.7027464198816952, 0.3917608374245498, -0.40505849281451556, 0.3917608374245498, 0.8, 0.1}};
+    for (const Ball& b : balls)
+        scene.add(std::make_unique<Sphere>(Vector3(b.x, b.y, b.z), b.r,
+                                           Material{SurfaceType::GGX(0.8), Texture::from_color(hsv_to_rgb(Color(b.hue, 1.0, 1.0))), Texture::black(),
+                                                    Texture::from_color(Color::from_one(b.rough))}));
+    scene.add(std::make_unique<Cuboid>(Aabb{Vector3(-5.0, -1.0, -5.0), Vector3(5.0, 0.0, 5.0)},
+                                       Material{SurfaceType::GGX(0.8), tex_path(a, MARBLE_DIFFUSE), Texture::black(), tex_path(a, MARBLE_ROUGHNESS)}));
+    scene.skybox = make_skybox(a, sky, Vector3::one());
+    // (the `while count < 0` loop of metal spheres draws nothing)
+    int count = 0;
+    while (count < 12) {  // diamonds lying on the floor
+        double px = rng.gen_range(-4.5, 4.5);
+        double py = 0.0;
+        double pz = rng.gen_range(-2.5, 4.5);
+        double s = rng.gen_range(0.7, 1.1);
+        double ry = rng.gen_range(-to_radians(180.0), to_radians(180.0));
+        if (scene.add_with_check_collisions(BvhMesh::from_mesh(ObjLoader::load(
+                a, "models/dia/dia.obj",
+                Matrix44::translate(px, py, pz) * Matrix44::scale_linear(s) * Matrix44::rotate_y(ry) * Matrix44::rotate_x(to_radians(40.35)), diamond_material()))))
+            count += 1;
+    }
+    count = 0;
+    while (count < 30) {  // diamonds floating in the air
+        double px = rng.gen_range(-4.5, 4.5);
+        double py = rng.gen_range(0.0, 4.0);
+        double pz = rng.gen_range(-4.5, 3.5);
+        double s = rng.gen_range(0.6, 1.1);
+        double ry = rng.gen_range(-to_radians(180.0), to_radians(180.0));
+        double rx = rng.gen_range(-to_radians(180.0), to_radians(180.0));
+        if (scene.add_with_check_collisions(BvhMesh::from_mesh(ObjLoader::load(
+                a, "models/dia/dia.obj", Matrix44::translate(px, py, pz) * Matrix44::scale_linear(s) * Matrix44::rotate_y(ry) * Matrix44::rotate_x(rx),
+                diamond_material()))))
+            count += 1;
+    }
+    return sc;
+}
+SceneAndCamera init_scene_rtcamp5(const AssetStore& a) { return scene_rtcamp5(a, "textures/cube/LancellottiChapel"); }
+
+// src/main.rs:502-722: four emissive spheres with a textured emission (multi-light NEE), 8 metal spheres and 20
+// diamonds placed by StdRng with add_with_check_collisions
+static SceneAndCamera scene_tbf3(const AssetStore& a, const std::string& sky) {
+    StdRng rng({870, 2000, 304, 1});
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 2.5, 9.0), Vector3(0.0, 1.5, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 19.0, LensShape::Circle, 0.18, 7.0);
+    Scene& scene = sc.scene;
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/klab_logo/klab_logo_triangle.obj", Matrix44::scale_linear(0.4) * Matrix44::translate(0.0, 3.1782, 2.0) * Matrix44::rotate_y(-0.5),
+        Material{SurfaceType::GGX(0.8), Texture::from_color(Color(0.4, 0.4, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.05))})));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/dia/dia.obj",
+        Matrix44::translate(1.3, 0.0, 2.2) * Matrix44::scale_linear(1.0) * Matrix44::rotate_y(-0.4) * Matrix44::rotate_x(to_radians(40.35)), diamond_material())));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/dia/dia.obj",
+        Matrix44::translate(-0.1, 0.0, 2.4) * Matrix44::scale_linear(1.0) * Matrix44::rotate_y(-1.4) * Matrix44::rotate_x(to_radians(40.35)), diamond_material())));
+    struct Light { double x, y, z, r; Color albedo, emission; };
+    const Light lights[4] = {{-1.0, 0.4, 4.0, 0.4, Color::one(), Color(3.0, 3.0, 1.1)},
+                             {-3.0, 0.4, -3.5, 0.4, Color(0.5, 1.0, 1.0), Color(1.0, 3.0, 3.5)},
+                             {4.0, 0.2, -4.5, 0.2, Color(0.3, 0.7, 1.0), Color(3.0, 3.0, 1.1)},
+                             {3.0, 0.2, -4.2, 0.2, Color(1.0, 0.7, 0.9), Color(2.0, 3.0, 1.0)}};
+    for (const Light& l : lights)
+        scene.add(std::make_unique<Sphere>(Vector3(l.x, l.y, l.z), l.r,
+                                           Material{SurfaceType::GGX(0.8), Texture::from_color(l.albedo), Texture::from_image(a.image(EARTH), l.emission),
+                                                    Texture::from_color(Color::from_one(0.01))}));
+    scene.add(std::make_unique<Cuboid>(Aabb{Vector3(-5.0, -1.0, -5.0), Vector3(5.0, 0.0, 5.0)},
+                                       Material{SurfaceType::GGX(0.8), tex_path(a, MARBLE_DIFFUSE), Texture::black(), tex_path(a, MARBLE_ROUGHNESS)}));
+    scene.skybox = make_skybox(a, sky, Vector3(2.0, 2.0, 3.0));
+    int count = 0;
+    while (count < 8) {  // metal spheres
+        double px = rng.gen_range(-3.0, 3.0);
+        double py = 0.0;
+        double pz = rng.gen_range(-5.0, 5.0);
+        double r = rng.gen_range(0.2, 0.4);
+        // the struct literal draws the roughness before the collision test decides (src/main.rs:659-667)
+        double rough = rng.gen_range(0.0, 0.2);
+        if (scene.add_with_check_collisions(std::make_unique<Sphere>(
+                Vector3(px, r + py, pz), r,
+                Material{SurfaceType::GGX(0.8), Texture::from_color(hsv_to_rgb(Color(0.2 + 0.1 * (double)count, 1.0, 1.0))), Texture::black(),
+                         Texture::from_color(Color::from_one(rough))})))
+            count += 1;
+    }
+    count = 0;
+    while (count < 20) {  // diamonds lying on the floor
+        double px = rng.gen_range(-4.0, 4.0);
+        double py = 0.0;
+        double pz = rng.gen_range(-5.0, 5.0);
+        double s = rng.gen_range(0.7, 1.1);
+        double ry = rng.gen_range(-to_radians(180.0), to_radians(180.0));
+        if (scene.add_with_check_collisions(BvhMesh::from_mesh(ObjLoader::load(
+                a, "models/dia/dia.obj",
+                Matrix44::translate(px, py, pz) * Matrix44::scale_linear(s) * Matrix44::rotate_y(ry) * Matrix44::rotate_x(to_radians(40.35)), diamond_material()))))
+            count += 1;
+    }
+    return sc;
+}
+SceneAndCamera init_scene_tbf3(const AssetStore& a) { return scene_tbf3(a, "textures/cube/LancellottiChapel"); }
+
 // BASELINE.md config 3 (builder-defined, not a scene of the reference): the
 // default scene plus the two fractal meshes with the materials the reference
 // gives them (src/main.rs:1171-1186 and :907-922), floating above the ring of
@@ -674,6 +865,10 @@ SceneAndCamera init_scene_by_name(const std::string& name, const AssetStore& a) 
     // the same two scenes under the (much smaller) Powerlines cubemap, so that they fit the committed asset pack
     if (name == "simple_pl") return scene_simple(a, "textures/cube/Powerlines");
     if (name == "material_examples_pl") return scene_material_examples(a, "textures/cube/Powerlines");
+    if (name == "rtcamp5") return init_scene_rtcamp5(a);
+    if (name == "tbf3") return init_scene_tbf3(a);
+    if (name == "rtcamp5_pl") return scene_rtcamp5(a, "textures/cube/Powerlines");
+    if (name == "tbf3_pl") return scene_tbf3(a, "textures/cube/Powerlines");
     if (name == "bvh_heavy") return init_scene_bvh_heavy(a);
     if (name == "diamond") return init_scene_diamond(a);
     throw std::runtime_error("unknown scene: " + name);
@@ -689,6 +884,10 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
     if (images) {
         if (rt || name == "diamond") { add(cube("textures/cube/Powerlines")); out.push_back("textures/2d/magic-circle3.png"); }
         if (name == "rtcamp6_v4") add(cube("textures/cube/Ryfjallet"));
+        if (name == "rtcamp5" || name == "tbf3" || name == "rtcamp5_pl" || name == "tbf3_pl") {
+            add(cube(name.size() > 3 && name.substr(name.size() - 3) == "_pl" ? "textures/cube/Powerlines" : "textures/cube/LancellottiChapel"));
+            add({EARTH, MARBLE_DIFFUSE, MARBLE_ROUGHNESS});
+        }
         if (name == "simple" || name == "material_examples" || name == "simple_pl" || name == "material_examples_pl") {
             add(cube(name.size() > 3 && name.substr(name.size() - 3) == "_pl" ? "textures/cube/Powerlines" : "textures/cube/LancellottiChapel"));
             out.push_back("textures/2d/checkered_diagonal_10_0.5_1.0_512.png");
@@ -699,6 +898,8 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
         if (name == "bvh_heavy") add({"models/fractal_icosahedron.obj", "models/fractal_dodecahedron.obj"});
         if (name == "rtcamp6_v4") out.push_back("models/fractal_icosahedron.obj");
         if (name == "diamond") out.push_back("models/round_brilliant.obj");
+        if (name == "rtcamp5" || name == "rtcamp5_pl") add({"models/bunny/bunny_face1000.obj", "models/bunny/bunny_face1000_flip.obj", "models/dia/dia.obj"});
+        if (name == "tbf3" || name == "tbf3_pl") add({"models/klab_logo/klab_logo_triangle.obj", "models/dia/dia.obj"});
     }
     return out;
 }

@@ -278,6 +278,22 @@ struct BvhScene {
     static std::unique_ptr<BvhScene> from_scene(Scene scene);
 };
 
+// rand 0.4.3 `StdRng` (= Isaac64Rng on 64-bit targets) as the scene builders use it (src/main.rs:253-254,431-482):
+// SeedableRng::from_seed(&[usize]) and Rng::gen_range(low, high) on f64.  Third-party code that is not in the
+// reference tree, restated from its published source; the generator core is pinned by rand's own
+// known-answer vectors (tests/test_host_and_abi.py), the f64 mapping is not (parity unpinned at that step).
+class StdRng {
+  public:
+    explicit StdRng(const std::vector<uint64_t>& seed);
+    uint64_t next_u64();
+    double next_f64();                       // [0, 1): 0x3FF0... | (u64 & (2^52 - 1)), minus 1.0
+    double gen_range(double low, double high);  // low + (high - low) * next_f64()
+  private:
+    void isaac64();
+    uint64_t rsl_[256], mem_[256], a_ = 0, b_ = 0, c_ = 0;
+    uint32_t cnt_ = 0;
+};
+
 // Scene authoring (src/main.rs): the default scene and the two builder-defined
 // benchmark scenes of BASELINE.md section 3.
 struct SceneAndCamera { Camera camera; Scene scene; };
@@ -285,6 +301,8 @@ SceneAndCamera init_scene_rtcamp6_v3_1(const AssetStore& a);  // src/main.rs:102
 SceneAndCamera init_scene_rtcamp6_v4(const AssetStore& a);    // src/main.rs:1155-1212
 SceneAndCamera init_scene_simple(const AssetStore& a);        // src/main.rs:54-131
 SceneAndCamera init_scene_material_examples(const AssetStore& a);  // src/main.rs:133-250
+SceneAndCamera init_scene_rtcamp5(const AssetStore& a);       // src/main.rs:252-499 (45 diamonds placed by StdRng)
+SceneAndCamera init_scene_tbf3(const AssetStore& a);          // src/main.rs:502-722 (four textured emitters)
 SceneAndCamera init_scene_bvh_heavy(const AssetStore& a);     // BASELINE config 3 (builder-defined)
 SceneAndCamera init_scene_diamond(const AssetStore& a);       // BASELINE config 4 (builder-defined)
 SceneAndCamera init_scene_by_name(const std::string& name, const AssetStore& a);

@@ -119,6 +119,19 @@ static Material make_material(const AssetStore* a, const hnmh_material* m) {
     return out;
 }
 
+// rand 0.4.3 StdRng as the scene builders use it: `count` u64 outputs (kind 0) or gen_range(low, high) f64 draws
+// (kind 1, written as doubles) after skipping `skip` outputs -- for the known-answer tests
+int hnmh_stdrng(const uint64_t* seed, uint32_t nseed, uint32_t skip, uint32_t count, int kind, double low, double high, void* out) {
+    if (!seed || !out) { g_err = "null argument"; return -1; }
+    StdRng rng(std::vector<uint64_t>(seed, seed + nseed));
+    for (uint32_t i = 0; i < skip; i++) rng.next_u64();
+    for (uint32_t i = 0; i < count; i++) {
+        if (kind == 0) ((uint64_t*)out)[i] = rng.next_u64();
+        else ((double*)out)[i] = rng.gen_range(low, high);
+    }
+    return 0;
+}
+
 void* hnmh_builder_create() { return new BuilderHandle(); }
 void hnmh_builder_destroy(void* b) { delete (BuilderHandle*)b; }
 int hnmh_builder_camera(void* b, const double* eye, const double* target, const double* y_up, double v_fov, int lens_shape,

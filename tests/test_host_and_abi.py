@@ -92,6 +92,65 @@ def test_other_scenes_build(hr, get_scene):
     assert s.counts()["emissions"] == 2 and s.desc.contents.skybox_intensity.tuple() == (0.0, 0.0, 0.0)
 
 
+def _stdrng(hr, seed, skip, count, kind=0, low=0.0, high=0.0):
+    from hanamaru_renderer_b200 import _ffi
+    seed = np.asarray(seed, np.uint64)
+    out = np.zeros(count, np.uint64 if kind == 0 else np.float64)
+    rc = _ffi.host().hnmh_stdrng(seed.ctypes.data_as(C.c_void_p), len(seed), skip, count, kind, low, high, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    return out
+
+
+def test_host_stdrng_known_answers(hr):
+    """The host's StdRng (scene authoring, src/main.rs:253-254) against rand 0.4.3's own test_rng_64_true_values."""
+    a = _stdrng(hr, [1, 23, 456, 7890, 12345], 0, 10)
+    assert a.tolist() == [547121783600835980, 14377643087320773276, 17351601304698403469, 1238879483818134882, 11952566807690396487,
+                          13970131091560099343, 4469761996653280935, 15552757044682284409, 6860251611068737823, 13722198873481261842]
+    b = _stdrng(hr, [12345, 67890, 54321, 9876], 10000, 10)
+    assert b.tolist() == [18143823860592706164, 8491801882678285927, 2699425367717515619, 17196852593171130876, 2606123525235546165,
+                          15790932315217671084, 596345674630742204, 9947027391921273664, 11788097613744130851, 10391409374914919106]
+    # gen_range(low, high) = low + (high - low) * next_f64(), next_f64 = (0x3FF0.. | u64 & (2^52-1)) - 1.0
+    u = _stdrng(hr, [870, 2000, 304, 2], 0, 6)
+    f = ((u & np.uint64(0xFFFFFFFFFFFFF)) | np.uint64(0x3FF0000000000000)).view(np.float64) - 1.0
+    g = _stdrng(hr, [870, 2000, 304, 2], 0, 6, kind=1, low=-4.5, high=4.5)
+    assert np.array_equal(g, -4.5 + 9.0 * f) and ((g >= -4.5) & (g < 4.5)).all()
+
+
+def test_rng_authored_scenes(hr, get_scene):
+    """init_scene_rtcamp5 / init_scene_tbf3 (src/main.rs:252-722): fixed elements + StdRng-placed ones that passed
+    add_with_check_collisions (src/scene.rs:366-376)."""
+    s = get_scene("rtcamp5_pl")
+    d = s.desc.contents
+    assert s.counts()["elements"] == 11 + 12 + 30 and s.counts()["emissions"] == 1
+    e = d.elements[d.emissions[0]]
+    assert e.kind == 0 and e.a.tuple() == (0.0, 0.5, -0.5) and d.materials[e.material].emission.image >= 0
+    assert d.materials[e.material].emission.color.tuple() == (5.0, 5.0, 2.0)
+    t = get_scene("tbf3_pl")
+    d = t.desc.contents
+    assert t.counts()["elements"] == 8 + 8 + 20 and t.counts()["emissions"] == 4
+    assert d.skybox_intensity.tuple() == (2.0, 2.0, 3.0)
+    # no two element boxes overlap among the RNG-placed elements and everything placed before them
+    def box(e):
+        if e.kind == 0:
+            c, r = np.array(e.a.tuple()), e.radius
+            return c - r, c + r
+        return np.array(e.a.tuple()), np.array(e.b.tuple())
+    for scene, first_random in ((s, 11), (t, 8)):
+        d = scene.desc.contents
+        boxes = [box(d.elements[i]) for i in range(d.num_elements)]
+        for i in range(first_random, d.num_elements):
+            for j in range(i):
+                lo_i, hi_i = boxes[i]
+                lo_j, hi_j = boxes[j]
+                assert not ((lo_i < hi_j).all() and (hi_i > lo_j).all()), (i, j)
+    # the metal spheres of tbf3: radius in [0.2, 0.4), resting on the floor, hue 0.2 + 0.1 * k
+    d = t.desc.contents
+    for k in range(8):
+        e = d.elements[8 + k]
+        assert e.kind == 0 and 0.2 <= e.radius < 0.4 and e.a.y == e.radius + 0.0
+        assert 0.0 <= d.materials[e.material].roughness.color.x < 0.2
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout not present")
 def test_pack_matches_reference_assets(hr):
     """The committed asset pack is exactly what the host builds from the reference checkout."""

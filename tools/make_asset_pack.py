@@ -32,11 +32,18 @@ MESHES = [
     "models/fractal_icosahedron.obj",
     "models/fractal_dodecahedron.obj",
     "models/round_brilliant.obj",
+    "models/bunny/bunny_face1000.obj",
+    "models/bunny/bunny_face1000_flip.obj",
+    "models/dia/dia.obj",
+    "models/klab_logo/klab_logo_triangle.obj",
 ]
 IMAGES = [
     "textures/2d/magic-circle3.png",
     "textures/2d/checkered_diagonal_10_0.5_1.0_512.png",
     "textures/2d/checkered_diagonal_10_0.1_0.6_512.png",
+    "textures/2d/earth_inverse_2048.jpg",
+    "textures/2d/MarbleFloorTiles2/TexturesCom_MarbleFloorTiles2_1024_c_diffuse.tiff",
+    "textures/2d/MarbleFloorTiles2/TexturesCom_MarbleFloorTiles2_1024_roughness.png",
 ] + ["textures/cube/Powerlines/%s.jpg" % f for f in ("posx", "negx", "posy", "negy", "posz", "negz")]
 
 

@@ -3,6 +3,7 @@
 
   rtcamp6_golden_480x270.png   the reference's only golden output, rtcamp6_1000x4spp.png (1920x1080,
                                1000 passes x 4 spp), box-downsampled 4x4 so that it is small enough to commit
+  rtcamp5_golden_480x270.png   rtcamp5.png (1920x1080), the same way
   oracle_vectors.npz           outputs of the oracle (both flavours agree on these) on fixed inputs:
                                regression pins for the oracle itself, and inputs the GPU tests replay
 Usage: python tools/make_golden.py [/root/reference]
@@ -25,6 +26,11 @@ def main():
     gold = np.asarray(Image.open(os.path.join(ref, "rtcamp6_1000x4spp.png")).convert("RGB"), dtype=np.float64)
     small = gold.reshape(270, 4, 480, 4, 3).mean(axis=(1, 3))
     Image.fromarray(np.clip(np.rint(small), 0, 255).astype(np.uint8)).save(os.path.join(out, "rtcamp6_golden_480x270.png"))
+
+    # the reference's second published image: init_scene_rtcamp5 (45 diamonds placed by StdRng::gen_range)
+    gold5 = np.asarray(Image.open(os.path.join(ref, "rtcamp5.png")).convert("RGB"), dtype=np.float64)
+    small5 = gold5.reshape(270, 4, 480, 4, 3).mean(axis=(1, 3))
+    Image.fromarray(np.clip(np.rint(small5), 0, 255).astype(np.uint8)).save(os.path.join(out, "rtcamp5_golden_480x270.png"))
 
     import hanamaru_renderer_b200 as hr
     from oracle_ffi import Oracle
