@@ -76,6 +76,8 @@ struct hnm_renderer {
     cudaStream_t rng_stream = nullptr;
     bool overlap = true;           // HNM_RNG_OVERLAP=0: generate on `stream`, in order (A/B and debugging)
     bool speculate = true;         // HNM_RNG_SPECULATE=0: no prefetch across hnm_render_passes calls
+    int rng_start_bounce = 1;      // HNM_RNG_START_BOUNCE=k: the prefetch is released after bounce k of the current batch (measured best of 0..4)
+    cudaEvent_t rng_gate = nullptr;
     uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
     CandLists cand = {};           // candidate lists of the rays in flight: camera rays [0, cap), shadow rays [cap, cap + scap)
@@ -240,7 +242,7 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
         hnm_renderer::GenSet& g = r->gen[s];
         g.valid = false;  // consumed by this batch
         // ---- prefetch the next batch into the other set (waits until that set's last consumer is done)
-        if (overlap && next_batch > 0) {
+        auto prefetch_next = [&]() -> int {
             hnm_renderer::GenSet& o = r->gen[s ^ 1];
             if (!(o.valid && o.sampling_first == next_first && o.batch == next_batch)) {
                 if (o.valid) r->gen_wasted++;
@@ -250,7 +252,10 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
                 HNM_CUDA(cudaEventRecord(o.ready, r->rng_stream));
                 o.ready_recorded = true;
             }
-        }
+            return 0;
+        };
+        const bool want_prefetch = overlap && next_batch > 0;
+        if (want_prefetch && r->rng_start_bounce <= 0) { int rc = prefetch_next(); if (rc) return rc; }
         bind_gen_set(P, g);
         launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
         for (int b = 1; b <= last; b++) {
@@ -267,6 +272,13 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             launch_timed(r, "shade_miss", [&] { k_shade_miss<<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_delta", [&] { k_shade_surf<false><<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_nee", [&] { k_shade_surf<true><<<grid, 256, 0, st>>>(P, b); });
+            if (want_prefetch && b == r->rng_start_bounce) {
+                // the generation of the next batch starts here: the thin late bounces leave the SMs under-used
+                HNM_CUDA(cudaEventRecord(r->rng_gate, st));
+                HNM_CUDA(cudaStreamWaitEvent(r->rng_stream, r->rng_gate, 0));
+                int rc = prefetch_next();
+                if (rc) return rc;
+            }
         }
         TraceJob sh = shadow_job(P, last);
         launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1);
@@ -316,6 +328,7 @@ void hnm_renderer_destroy(hnm_renderer* r) {
         if (g.ready) cudaEventDestroy(g.ready);
         if (g.released) cudaEventDestroy(g.released);
     }
+    if (r->rng_gate) cudaEventDestroy(r->rng_gate);
     if (r->rng_stream) cudaStreamDestroy(r->rng_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
@@ -349,6 +362,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
+    if (const char* e = getenv("HNM_RNG_START_BOUNCE")) r->rng_start_bounce = atoi(e);
     uint32_t ntiles = (height + sh.tile_rows - 1) / sh.tile_rows;
     uint32_t tiles_per_rank = (ntiles + sh.num_ranks - 1) / sh.num_ranks;
     r->padded_rows = tiles_per_rank * sh.tile_rows;  // equal on every rank (all-gather)
@@ -412,6 +426,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
             return bail(HNM_ERR_CUDA);
         }
     }
+    if (cudaEventCreateWithFlags(&r->rng_gate, cudaEventDisableTiming) != cudaSuccess) { set_error(HNM_ERR_CUDA, "cudaEventCreate failed"); return bail(HNM_ERR_CUDA); }
     bind_gen_set(P, r->gen[0]);
     if ((rc = dev_alloc(A, &P.hit_t, cap))) return bail(rc);
     if ((rc = dev_alloc(A, &P.hit_u, cap))) return bail(rc);

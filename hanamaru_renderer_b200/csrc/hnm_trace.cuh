@@ -317,6 +317,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         float4 m0 = __ldg(np), m1 = __ldg(np + 1), m2 = __ldg(np + 2);
                         int2 m3 = __ldg(reinterpret_cast<const int2*>(np + 3));
                         if (STATS) n_nodes++;
+
                         float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
                         float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
                         float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
