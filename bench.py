@@ -176,7 +176,8 @@ def run_ours(args):
     assets = hr.AssetStore.from_pack()
     scene = hr.build_scene(SCENE, assets)
     dev = hr.DeviceScene(scene, local)
-    shard = (rank, world, hd.DEFAULT_TILE_ROWS) if use_dist else None
+    tile_rows = int(os.environ.get("HNM_TILE_ROWS", hd.DEFAULT_TILE_ROWS))
+    shard = (rank, world, tile_rows) if use_dist else None
     ctx = hr.RenderContext(dev, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
     P = args.pps
     K, Wm = args.steps, args.warmup

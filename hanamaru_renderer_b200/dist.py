@@ -8,7 +8,7 @@ torch.distributed is plumbing only; the gather works on any backend (NCCL on GPU
 """
 import numpy as np
 
-DEFAULT_TILE_ROWS = 8
+DEFAULT_TILE_ROWS = 4  # measured at N = 8, 1080p: 2 / 4 / 8 rows within 1.5 %; small tiles balance glass vs sky rows
 
 
 def padded_rows(height, num_ranks, tile_rows=DEFAULT_TILE_ROWS):
