@@ -183,6 +183,38 @@ def test_exact_ties_follow_reference_order(hr, core, oracle, assets):
     assert set(np.unique(got["element"]).tolist()) >= {-1, 1, 2, 4}
 
 
+def test_candidate_list_overflow_falls_back_to_exact_traversal(hr, core, oracle, assets):
+    """k_trace keeps at most 8 candidates per ray; a ray with more (here: 24 coincident copies of every triangle, all
+    tied at the same distance) is re-traced by k_confirm with the plain exact traversal.  Same bits either way, for
+    single rays and for whole paths (NEE shadow rays through the stack included)."""
+    rng = np.random.default_rng(11)
+    v = np.array([[-2, 0.5, -2], [2, 0.5, -2], [2, 0.5, 2], [-2, 0.5, 2], [0, 1.5, 0]], np.float64)
+    f = np.array([[0, 1, 2], [0, 2, 3], [0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.uint32)
+    f = np.concatenate([f] * 24)
+    b = hr.SceneBuilder(assets)
+    b.camera((0, 3, 6), (0, 0.5, 0), aperture=0.05, focus_distance=6.0)
+    b.add_mesh(v, f, hr.SceneBuilder.material(hr.SURFACE_GGX, param=0.8, roughness=0.3, albedo=(0.8, 0.6, 0.4)))
+    b.add_sphere((0.5, 3.0, 0.5), 0.3, hr.SceneBuilder.material(hr.SURFACE_DIFFUSE, albedo=(0, 0, 0), emission=(20, 20, 20)))
+    b.add_cuboid((-5, -1, -5), (5, 0, 5), hr.SceneBuilder.material(hr.SURFACE_DIFFUSE, albedo=(0.7, 0.7, 0.7)))
+    b.skybox()
+    scene = b.finish()
+    dev = hr.DeviceScene(scene, 0)
+    n = 50000
+    o = rng.normal(size=(n, 3)) * [1, 0.3, 1] + [0, 4, 0]
+    d = rng.uniform(-1.5, 1.5, size=(n, 3)) * [1, 0, 1] + [0, 0.8, 0] - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    got, want = dev.intersect(o, d), oracle.intersect(scene, o, d)
+    for fld in got.dtype.names:
+        assert field_equal(got[fld], want[fld]), fld
+    assert (got["element"] == 0).mean() > 0.3          # many rays do hit the 24-fold mesh
+    ctx = render_gpu(hr, dev, scene, 96, 54, hr.MODE_PATHTRACING, 1, 2)
+    acc, cnt = oracle.render(scene, 96, 54, hr.MODE_PATHTRACING, 1, 2)
+    assert np.array_equal(bits(ctx.read_accum()), bits(acc))
+    c = ctx.counters()
+    assert (c["segments"], c["shadow_rays"]) == (cnt["segments"], cnt["shadow_rays"])
+    ctx.close()
+
+
 # ---------------------------------------------------------------------------------------- debug passes
 @pytest.mark.parametrize("w,h", [(480, 270), (1920, 1080)])
 def test_debug_passes_bit_exact(hr, core, oracle, get_scene, get_device_scene, w, h):
@@ -396,3 +428,19 @@ def test_full_size_properties(hr, core, oracle, get_scene, get_device_scene):
     assert ctx.counters()["paths"] == 4 * w * h * 4
     ctx.close()
     assert np.isfinite(a4).all() and (a4 >= 0).all()
+
+
+def test_4k_bands_bit_exact(hr, core, oracle, get_scene, get_device_scene):
+    """BASELINE config 5 resolution (3840x2160, 33.2 M paths per pass) on one GPU: bands of rows against the oracle
+    (top / sky, the armadillo ring, floor), the whole-image path count, and the resolved image of those bands' interior."""
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    w, h = 3840, 2160
+    ctx = render_gpu(hr, dev, scene, w, h, hr.MODE_PATHTRACING, 1, 1)
+    got = ctx.read_accum()
+    c = ctx.counters()
+    assert c["paths"] == w * h * 4
+    for r0 in (0, 1000, 1400, 2152):
+        want, _ = oracle.render(scene, w, h, hr.MODE_PATHTRACING, 1, 1, rows=(r0, r0 + 8), counters=False)
+        assert np.array_equal(bits(got[r0:r0 + 8]), bits(want[r0:r0 + 8])), r0
+    assert np.isfinite(got).all()
+    ctx.close()
