@@ -61,7 +61,7 @@ def main():
         md += ["## Launch list (`--metrics gpu__time_duration.sum`; cold-cache, serialised: compare SHARES)", "", table, "",
                "total %.3f ms over the captured launches" % T, ""]
     traffic = {}
-    for name, key in (("trace", "trace"), ("isaac", "isaac_raygen"), ("shade", "shade_nee")):
+    for name, key in (("trace", "trace"), ("confirm", "confirm"), ("isaac", "isaac_raygen"), ("shade", "shade_nee")):
         rep = os.path.join(src, "prof_%s_%s.ncu-rep" % (name, rnd))
         if not os.path.exists(rep):
             continue
@@ -76,7 +76,8 @@ def main():
             pass
     open(os.path.join(dst, "ncu_%s.md" % rnd), "w").write("\n".join(md) + "\n")
     # per-launch DRAM traffic of the first captured launch of each kernel, for bench.py's roofline.traffic
-    json.dump({k: v[0] for k, v in traffic.items()}, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
+    # (shade: the second capture is the NEE kernel, k_shade_surf<1>)
+    json.dump({k: (v[1] if k == "shade_nee" and len(v) > 1 else v[0]) for k, v in traffic.items()}, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
     print("\n".join(md))
 
 
