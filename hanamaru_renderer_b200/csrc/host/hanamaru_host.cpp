@@ -820,6 +820,48 @@ static SceneAndCamera scene_tbf3(const AssetStore& a, const std::string& sky) {
 }
 SceneAndCamera init_scene_tbf3(const AssetStore& a) { return scene_tbf3(a, "textures/cube/LancellottiChapel"); }
 
+// src/main.rs:804-925: 100 GGX spheres and FIVE emissive ones placed by StdRng (five shadow rays per NEE event)
+// around a refractive fractal
+static SceneAndCamera scene_rtcamp6_v2(const AssetStore& a, const std::string& sky) {
+    StdRng rng({870, 2000, 304, 2});
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(-5.0, -1.0, 0.0), Vector3(0.0, 0.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 10.0, LensShape::Circle, 0.2 * 0.0, 8.8);
+    Scene& scene = sc.scene;
+    scene.skybox = make_skybox(a, sky, Vector3::from_one(0.5));
+    int count = 0;
+    while (count < 100) {
+        double px = rng.gen_range(-0.5, 2.0);
+        double py = rng.gen_range(-2.0, 2.0);
+        double pz = rng.gen_range(-2.0, 2.0);
+        double s = 0.1;
+        // the struct literal draws hue and roughness before the collision test decides (src/main.rs:870-880)
+        double hue = rng.gen_range(0.0, 1.0);
+        double rough = rng.gen_range(0.0, 1.0);
+        if (scene.add_with_check_collisions(std::make_unique<Sphere>(
+                Vector3(px, py, pz), s,
+                Material{SurfaceType::GGX(0.9), Texture::from_color(hsv_to_rgb(Color(hue, 1.0, 1.0))), Texture::black(), Texture::from_color(Color::from_one(rough))})))
+            count += 1;
+    }
+    count = 0;
+    while (count < 5) {
+        double px = rng.gen_range(-0.2, 0.5);
+        double py = rng.gen_range(-1.0, 1.0);
+        double pz = rng.gen_range(-1.0, 1.0);
+        double s = 0.1;
+        double hue = rng.gen_range(0.0, 1.0);
+        double rough = rng.gen_range(0.0, 1.0);
+        if (scene.add_with_check_collisions(std::make_unique<Sphere>(
+                Vector3(px, py, pz), s,
+                Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(hsv_to_rgb(Color(hue, 1.0, 1.0)) * 10.0), Texture::from_color(Color::from_one(rough))})))
+            count += 1;
+    }
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/fractal_dodecahedron.obj", Matrix44::scale_linear(1.0) * Matrix44::translate(0.0, 0.0, 0.0) * Matrix44::rotate_y(0.0),
+        Material{SurfaceType::Refraction(1.5), Texture::from_color(Color(0.7, 0.7, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.1))})));
+    return sc;
+}
+SceneAndCamera init_scene_rtcamp6_v2(const AssetStore& a) { return scene_rtcamp6_v2(a, "textures/cube/Ryfjallet"); }
+
 // BASELINE.md config 3 (builder-defined, not a scene of the reference): the
 // default scene plus the two fractal meshes with the materials the reference
 // gives them (src/main.rs:1171-1186 and :907-922), floating above the ring of
@@ -865,6 +907,8 @@ SceneAndCamera init_scene_by_name(const std::string& name, const AssetStore& a) 
     // the same two scenes under the (much smaller) Powerlines cubemap, so that they fit the committed asset pack
     if (name == "simple_pl") return scene_simple(a, "textures/cube/Powerlines");
     if (name == "material_examples_pl") return scene_material_examples(a, "textures/cube/Powerlines");
+    if (name == "rtcamp6_v2") return init_scene_rtcamp6_v2(a);
+    if (name == "rtcamp6_v2_pl") return scene_rtcamp6_v2(a, "textures/cube/Powerlines");
     if (name == "rtcamp5") return init_scene_rtcamp5(a);
     if (name == "tbf3") return init_scene_tbf3(a);
     if (name == "rtcamp5_pl") return scene_rtcamp5(a, "textures/cube/Powerlines");
@@ -883,7 +927,8 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
     bool rt = (name == "rtcamp6" || name == "rtcamp6_v3_1" || name == "bvh_heavy");
     if (images) {
         if (rt || name == "diamond") { add(cube("textures/cube/Powerlines")); out.push_back("textures/2d/magic-circle3.png"); }
-        if (name == "rtcamp6_v4") add(cube("textures/cube/Ryfjallet"));
+        if (name == "rtcamp6_v4" || name == "rtcamp6_v2") add(cube("textures/cube/Ryfjallet"));
+        if (name == "rtcamp6_v2_pl") add(cube("textures/cube/Powerlines"));
         if (name == "rtcamp5" || name == "tbf3" || name == "rtcamp5_pl" || name == "tbf3_pl") {
             add(cube(name.size() > 3 && name.substr(name.size() - 3) == "_pl" ? "textures/cube/Powerlines" : "textures/cube/LancellottiChapel"));
             add({EARTH, MARBLE_DIFFUSE, MARBLE_ROUGHNESS});
@@ -897,6 +942,7 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
         if (rt) add({"models/bunny/bunny_wired_300.obj", "models/box.obj", "models/picture_frame.obj", "models/armadilo_1000.obj"});
         if (name == "bvh_heavy") add({"models/fractal_icosahedron.obj", "models/fractal_dodecahedron.obj"});
         if (name == "rtcamp6_v4") out.push_back("models/fractal_icosahedron.obj");
+        if (name == "rtcamp6_v2" || name == "rtcamp6_v2_pl") out.push_back("models/fractal_dodecahedron.obj");
         if (name == "diamond") out.push_back("models/round_brilliant.obj");
         if (name == "rtcamp5" || name == "rtcamp5_pl") add({"models/bunny/bunny_face1000.obj", "models/bunny/bunny_face1000_flip.obj", "models/dia/dia.obj"});
         if (name == "tbf3" || name == "tbf3_pl") add({"models/klab_logo/klab_logo_triangle.obj", "models/dia/dia.obj"});

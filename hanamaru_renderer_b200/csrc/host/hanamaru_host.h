@@ -301,6 +301,7 @@ SceneAndCamera init_scene_rtcamp6_v3_1(const AssetStore& a);  // src/main.rs:102
 SceneAndCamera init_scene_rtcamp6_v4(const AssetStore& a);    // src/main.rs:1155-1212
 SceneAndCamera init_scene_simple(const AssetStore& a);        // src/main.rs:54-131
 SceneAndCamera init_scene_material_examples(const AssetStore& a);  // src/main.rs:133-250
+SceneAndCamera init_scene_rtcamp6_v2(const AssetStore& a);    // src/main.rs:804-925 (105 StdRng-placed spheres, five emitters)
 SceneAndCamera init_scene_rtcamp5(const AssetStore& a);       // src/main.rs:252-499 (45 diamonds placed by StdRng)
 SceneAndCamera init_scene_tbf3(const AssetStore& a);          // src/main.rs:502-722 (four textured emitters)
 SceneAndCamera init_scene_bvh_heavy(const AssetStore& a);     // BASELINE config 3 (builder-defined)

@@ -143,6 +143,9 @@ def test_rng_authored_scenes(hr, get_scene):
                 lo_i, hi_i = boxes[i]
                 lo_j, hi_j = boxes[j]
                 assert not ((lo_i < hi_j).all() and (hi_i > lo_j).all()), (i, j)
+    v2 = get_scene("rtcamp6_v2_pl")
+    assert v2.counts()["elements"] == 100 + 5 + 1 and v2.counts()["emissions"] == 5
+    assert v2.desc.contents.skybox_intensity.tuple() == (0.5, 0.5, 0.5)
     # the metal spheres of tbf3: radius in [0.2, 0.4), resting on the floor, hue 0.2 + 0.1 * k
     d = t.desc.contents
     for k in range(8):
