@@ -131,6 +131,7 @@ struct DScene {
     const float4* elemf;       // 4 x float4 per element for the f32 pre-tests (hnm_trace.cuh): sphere = (centre, radius);
                                // cuboid = box rounded outward (lo, hi), box rounded inward (lo, hi)
     const DMaterial* materials;
+    const double* unorm8;      // [256]: i / 255.0
     const DImage* images;
     const DImage* sky_faces;  // px nx py ny pz nz (device memory: indexed at run time)
     const uint32_t* emissions;
@@ -304,30 +305,47 @@ HNM_D Hit trace(const DScene& sc, D3 o, D3 dir, TraceStats* st) {
 }
 
 // ---------------------------------------------------------------- src/texture.rs, src/color.rs
-HNM_D D3 sample_nearest_screen(const DImage& im, uint32_t x, uint32_t y) {  // src/texture.rs:59-63
+// `(texel as f64) / 255.0` (src/color.rs:18-24) for the 256 possible texel values, computed on the host with the same
+// correctly rounded IEEE division: a 2 KB table in global memory (L1-resident, DScene::unorm8) instead of twelve f64
+// divisions per bilinear sample (ncu, round 1: 9 % of the instructions of k_shade_surf<NEE>)
+HNM_D uchar4 texel_screen(const DImage& im, uint32_t x, uint32_t y) {  // src/texture.rs:59-63
     x = clamp_u32(x, 0u, im.width - 1u);
     y = clamp_u32(im.height - y - 1u, 0u, im.height - 1u);  // wraps at y == height, then clamps
-    uchar4 p = tex2D<uchar4>(im.tex, (float)x + 0.5f, (float)y + 0.5f);
-    return d3((double)p.x / 255.0, (double)p.y / 255.0, (double)p.z / 255.0);  // src/color.rs:18-24
+    return tex2D<uchar4>(im.tex, (float)x + 0.5f, (float)y + 0.5f);
 }
-// One out-of-line copy per module: (1) it is called from every shading kernel, and (2) ptxas 12.9 miscompiled an
-// inlined copy inside k_intersect_batch (blue channel of the 4-texel blend wrong; the out-of-line call is exact --
-// tests/test_gpu_parity.py::test_intersect_batch_matches_oracle pins it).
-__device__ __noinline__ D3 sample_bilinear(double gamma, DImage im, double u, double v) {  // src/texture.rs:29-49
-    double x = u * (double)im.width;
-    double y = v * (double)im.height;
-    double x1 = floor(x), y1 = floor(y);
-    double x2 = x1 + 1.0, y2 = y1 + 1.0;
-    D3 p11 = sample_nearest_screen(im, f64_as_u32(x1), f64_as_u32(y1));
-    D3 p12 = sample_nearest_screen(im, f64_as_u32(x1), f64_as_u32(y2));
-    D3 p21 = sample_nearest_screen(im, f64_as_u32(x2), f64_as_u32(y1));
-    D3 p22 = sample_nearest_screen(im, f64_as_u32(x2), f64_as_u32(y2));
-    D3 g = (p11 * (x2 - x) * (y2 - y) + p21 * (x - x1) * (y2 - y) + p12 * (x2 - x) * (y - y1) + p22 * (x - x1) * (y - y1)) /
-           ((x2 - x1) * (y2 - y1));
-    return d3(dm::pow(g.x, gamma), dm::pow(g.y, gamma), dm::pow(g.z, gamma));  // gamma_to_linear
+// One out-of-line copy per module: it is called from every shading kernel.  ptxas 12.9 (sm_100a, -O3) has produced a
+// wrong THIRD component of this function's result in some kernels for some shapes of this code (PTX correct, SASS
+// wrong); tests/test_gpu_parity.py pins every kernel that calls it bit-for-bit.
+__device__ __noinline__ void sample_bilinear_to(const double* __restrict__ unorm8, double gamma, DImage im, double u, double v,
+                                                double* out) {  // src/texture.rs:29-49
+    const double x = u * (double)im.width;
+    const double y = v * (double)im.height;
+    const double x1 = floor(x), y1 = floor(y);
+    const double x2 = x1 + 1.0, y2 = y1 + 1.0;
+    const uchar4 t11 = texel_screen(im, f64_as_u32(x1), f64_as_u32(y1));
+    const uchar4 t12 = texel_screen(im, f64_as_u32(x1), f64_as_u32(y2));
+    const uchar4 t21 = texel_screen(im, f64_as_u32(x2), f64_as_u32(y1));
+    const uchar4 t22 = texel_screen(im, f64_as_u32(x2), f64_as_u32(y2));
+    const double ax = x2 - x, bx = x - x1, ay = y2 - y, by = y - y1;
+    const double den = (x2 - x1) * (y2 - y1);
+    // per channel, in the reference's order: ((p11*(x2-x))*(y2-y) + (p21*(x-x1))*(y2-y) + (p12*(x2-x))*(y-y1) + (p22*(x-x1))*(y-y1)) / den
+    const unsigned char c11[3] = {t11.x, t11.y, t11.z}, c12[3] = {t12.x, t12.y, t12.z};
+    const unsigned char c21[3] = {t21.x, t21.y, t21.z}, c22[3] = {t22.x, t22.y, t22.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double p11 = __ldg(unorm8 + c11[k]), p12 = __ldg(unorm8 + c12[k]);
+        const double p21 = __ldg(unorm8 + c21[k]), p22 = __ldg(unorm8 + c22[k]);
+        const double g = (p11 * ax * ay + p21 * bx * ay + p12 * ax * by + p22 * bx * by) / den;
+        out[k] = dm::pow(g, gamma);  // gamma_to_linear
+    }
+}
+HNM_D D3 sample_bilinear(const double* unorm8, double gamma, DImage im, double u, double v) {
+    double r[3];
+    sample_bilinear_to(unorm8, gamma, im, u, v, r);
+    return d3(r[0], r[1], r[2]);
 }
 HNM_D D3 texture_sample(const DScene& sc, const DTexture& t, double u, double v) {  // src/texture.rs:108-114
-    if (t.image >= 0) return sample_bilinear(sc.gamma, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
+    if (t.image >= 0) return sample_bilinear(sc.unorm8, sc.gamma, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
     return d3(t.r, t.g, t.b);
 }
 // src/scene.rs:295-319
@@ -348,7 +366,7 @@ HNM_D D3 skybox_sample(const DScene& sc, D3 direction) {
     // sample_bilinear_0center (src/texture.rs:22-26)
     // the six faces live in device memory: a run-time index into a kernel-PARAMETER array makes nvcc 12.9 spill the
     // parameter struct to local memory, and the copy it generated in one kernel was wrong (blue intensity garbage)
-    D3 c = sample_bilinear(sc.gamma, sc.sky_faces[face], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
+    D3 c = sample_bilinear(sc.unorm8, sc.gamma, sc.sky_faces[face], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
     return d3(sc.sky_r, sc.sky_g, sc.sky_b) * c;
 }
 

@@ -530,6 +530,11 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
         mats[i].has_image = (m.albedo.image >= 0 || m.emission.image >= 0 || m.roughness.image >= 0) ? 1 : 0;
     }
     if ((rc = upload(s, mats, &s->d.materials))) return bail(rc);
+    {
+        std::vector<double> lut(256);
+        for (int i = 0; i < 256; i++) lut[i] = (double)i / 255.0;  // src/color.rs:18-24, one correctly rounded division each
+        if ((rc = upload(s, lut, &s->d.unorm8))) return bail(rc);
+    }
     std::vector<DImage> imgs(desc->num_images);
     for (uint32_t i = 0; i < desc->num_images; i++) {
         const hnm_image& im = desc->images[i];
