@@ -335,7 +335,8 @@ __device__ __noinline__ void sample_bilinear_to(const double* __restrict__ unorm
     for (int k = 0; k < 3; k++) {
         const double p11 = __ldg(unorm8 + c11[k]), p12 = __ldg(unorm8 + c12[k]);
         const double p21 = __ldg(unorm8 + c21[k]), p22 = __ldg(unorm8 + c22[k]);
-        const double g = (p11 * ax * ay + p21 * bx * ay + p12 * ax * by + p22 * bx * by) / den;
+        const double num = p11 * ax * ay + p21 * bx * ay + p12 * ax * by + p22 * bx * by;
+        const double g = den == 1.0 ? num : num / den;  // den = ((x1 + 1) - x1) * ((y1 + 1) - y1) is exactly 1 below 2^53
         out[k] = dm::pow(g, gamma);  // gamma_to_linear
     }
 }
