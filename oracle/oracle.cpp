@@ -12,10 +12,14 @@
 //   * rand's own ISAAC-64 known-answer vectors (tests/test_oracle.py),
 //   * the reference's golden image rtcamp6_1000x4spp.png (tests/golden/, made by
 //     tools/make_golden.py), statistically,
+//   * the reference's other published image rtcamp5.png: its 42 diamonds are placed by StdRng::gen_range, and the
+//     host's restatement of rand 0.4.3 reproduces the layout diamond for diamond -- that pins the u64->f64 mapping
+//     (tests/test_oracle.py::test_rtcamp5_layout_matches_published_image),
 //   * hand-checked vectors for the pure functions (tests/test_oracle.py).
 // Parity UNPINNED at two steps only, both third-party code absent from the tree:
-// rand 0.4.3's u64->f64 mapping / tuple order (restated from its published
-// source), and the image crate's JPEG decoder (decoded texels are inputs here).
+// the order of the two draws of rand 0.4.3's `gen::<(f64, f64)>()` (its tuple_impl! macro builds the tuple
+// expression `(rng.gen(), rng.gen())`, which Rust evaluates left to right; restated, not testable with an image),
+// and the image crate's JPEG decoder (decoded texels are inputs here).
 //
 // Input is the same flat hnm_scene_desc the CUDA core consumes (the host builds
 // the BVH with the reference's algorithm and flattens it in DFS order, so the
