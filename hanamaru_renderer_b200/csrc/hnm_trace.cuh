@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     const uint32_t n0 = *A.job[0].count;
     const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
     const uint32_t ntot = n0 + n1;
-    const float W = 4.76837158203125e-07f;  // 2^-21, see hnm_device.cuh: trace()
+    const float WLO = 1.0f - 4.76837158203125e-07f, WUP = 1.0f + 4.76837158203125e-07f;  // 1 -+ 2^-21, see hnm_device.cuh: trace()
 
     int32_t stack[HNM_STACK];
     int sp = 0;
@@ -328,8 +328,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
                         float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
                         float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
-                        float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
-                        float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
+                        // relative margin for the f32 roundings: widen towards 0 / +inf.  (For a negative bound the product
+                        // moves the other way, by 2^-21 relative -- irrelevant: a box with tmax < 0 is behind the ray either
+                        // way, and a negative tmin only ever meets the tests `<= up` and `<= best_ub` with non-negative right sides.)
+                        float lo0 = tmin0 * WLO, up0 = tmax0 * WUP;
+                        float lo1 = tmin1 * WLO, up1 = tmax1 * WUP;
                         const bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= best_ub);
                         const bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= best_ub);
                         const bool swap = lo1 < lo0;
