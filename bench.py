@@ -251,13 +251,13 @@ def run_ours(args):
         #   isaac    : write 32-word tail 256 + first-bounce ray 76 + L 24 + cursor 1                = 357 B / path
         #   trace    : read origin + direction 48 (+ 4 tmax for shadow rays); write list header 8 + 8 per candidate
         #              (1.1 candidates per ray measured)                                             = 65 / 69 B per ray
-        #   confirm  : read ray 48 + header 8 + 8 per candidate; write hit 32 (+ 4 queue entry for camera rays);
-        #              the f64 triangles it tests come from the L2-resident scene                    = 101 / 97 B per ray
+        #   confirm  : camera rays: read ray 48 + header 8 + 8 per candidate; write hit 32 + queue entry 4; the f64
+        #              triangles it tests come from the L2-resident scene (shadow rays: inside nee_resolve) = 101 B per ray
         #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17; write next ray 76 (survivors; counted
         #              for all) + event 76 + shadow ray 92                                           = 373 B / NEE event
         cand = 1.1
         per_unit = {"trace": ((56.0 + 8 * cand) * seg / max(1, seg + sh) + (60.0 + 8 * cand) * sh / max(1, seg + sh), seg + sh),
-                    "confirm": ((92.0 + 8 * cand) * seg / max(1, seg + sh) + (88.0 + 8 * cand) * sh / max(1, seg + sh), seg + sh),
+                    "confirm": (92.0 + 8 * cand, seg),
                     "shade_nee": (373.0, nee_events),
                     "isaac_raygen": (357.0, paths_p), "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p),
                     "shade_delta": (4 + 48 + 24 + 4 + 32 + 17 + 48 + 76.0, seg - nee_events)}

@@ -170,7 +170,7 @@ TraceJob shadow_job(const RParams& P, int bounce) {
     TraceJob j;
     memset(&j, 0, sizeof(j));
     for (int k = 0; k < 6; k++) j.ray[k] = P.sray[k];
-    j.hit_t = P.sh_t; j.hit_u = P.sh_u; j.hit_v = P.sh_v; j.hit_id = P.sh_id;
+    // no hit record: k_nee_resolve confirms these rays itself
     j.count = &P.counters[bounce * C_STRIDE + C_SHADOW];
     j.tmax = P.s_tmax;
     j.slot0 = P.cap;  // the shadow rays' candidate lists follow the camera rays'
@@ -184,7 +184,19 @@ const char* trace_name(hnm_renderer* r, int bounce) {
     return (r->per_bounce_names && bounce >= 0 && bounce <= 12) ? names[bounce] : "trace";
 }
 
-void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const TraceJob* j1, uint32_t* work, int stat_segments) {
+void launch_nee_resolve(hnm_renderer* r, int bounce) {
+    const int grid = r->sm_count * 4;
+    RParams& P = r->P;
+    cudaStream_t st = r->stream;
+    CandLists cand = r->cand;
+    if (r->trace_stats) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<true><<<grid, 256, 0, st>>>(P, cand, bounce); });
+    else launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false><<<grid, 256, 0, st>>>(P, cand, bounce); });
+}
+
+// k_trace over one or two ray lists; k_confirm for the FIRST list if `confirm_first` (a shadow-ray list is confirmed by
+// its consumer, k_nee_resolve)
+void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const TraceJob* j1, uint32_t* work, int stat_segments,
+                  bool confirm_first = true) {
     TraceArgs A;
     memset(&A, 0, sizeof(A));
     A.job[0] = *j0;
@@ -200,12 +212,14 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     const int cgrid = r->sm_count * 8;
     DScene sc = r->P.sc;
     cudaStream_t st = r->stream;
+    TraceArgs C = A;
+    C.njobs = 1;
     if (r->trace_stats) {
         launch_timed(r, name, [&] { k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
-        launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, A); });
+        if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, C); });
     } else {
         launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
-        launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, A); });
+        if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, C); });
     }
 }
 
@@ -265,7 +279,7 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             if (b > 1) {
                 TraceJob sh = shadow_job(P, b - 1);
                 launch_trace(r, trace_name(r, b), &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
-                launch_timed(r, "nee_resolve", [&] { k_nee_resolve<<<grid, 256, 0, st>>>(P, b - 1); });
+                launch_nee_resolve(r, b - 1);
             } else {
                 launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
             }
@@ -281,8 +295,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             }
         }
         TraceJob sh = shadow_job(P, last);
-        launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1);
-        launch_timed(r, "nee_resolve", [&] { k_nee_resolve<<<grid, 256, 0, st>>>(P, last); });
+        launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1, false);
+        launch_nee_resolve(r, last);
         launch_timed(r, "accumulate", [&] { k_accumulate<<<grid, 256, 0, st>>>(P); });
         HNM_CUDA(cudaEventRecord(g.released, st));
         g.released_recorded = true;
@@ -448,10 +462,6 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         if ((rc = dev_alloc(A, &P.s_bsdf, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.s_g, scap))) return bail(rc);
         if ((rc = dev_alloc(A, &P.s_tmax, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.sh_t, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.sh_u, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.sh_v, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.sh_id, scap))) return bail(rc);
     }
     {
         size_t nl = cap + (mode == HNM_MODE_PATHTRACING ? cap * std::max<uint32_t>(scene->num_emissions, 1) : 0);
@@ -478,7 +488,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         cudaFuncSetAttribute(k_shade_miss, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_shade_surf<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_shade_surf<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-        cudaFuncSetAttribute(k_nee_resolve, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_nee_resolve<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_batch_begin, cudaFuncAttributePreferredSharedMemoryCarveout, c);
     }

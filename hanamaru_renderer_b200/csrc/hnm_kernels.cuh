@@ -85,7 +85,6 @@ struct RParams {
     double* ev_thr[3]; double* ev_albedo[3]; double* ev_emission[3]; uint32_t* ev_pid;
     double* sray[6]; double* s_pos[3]; double* s_bsdf; double* s_g;
     float* s_tmax;        // distance from the shading point to the light sample: the shadow query is bounded (k_trace)
-    double* sh_t; double* sh_u; double* sh_v; uint2* sh_id;
     uint32_t* counters;
     unsigned long long* stats;
     double* accum;        // [padded_rows * W * 3]
@@ -548,21 +547,29 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
     }
 }
 
-// src/renderer.rs:282-295 + :183,196 for the NEE events of one bounce, after their shadow rays were traced
-__global__ void __launch_bounds__(256) k_nee_resolve(RParams P, int bounce) {
+// src/renderer.rs:282-295 + :183,196 for the NEE events of one bounce, after k_trace listed the candidates of their
+// shadow rays: exact closest hit of every shadow ray (confirm_ray -- its only consumer is right here, so no hit record
+// goes through memory), visibility test, light contribution, radiance update.
+template <bool STATS>
+__global__ void __launch_bounds__(256) k_nee_resolve(RParams P, CandLists cand, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_EVENTS];
     const uint32_t nl = P.sc.num_emissions;
     const DScene& sc = P.sc;
+    uint32_t n_prims = 0;
     for (uint32_t ev = blockIdx.x * blockDim.x + threadIdx.x; ev < n; ev += gridDim.x * blockDim.x) {
         D3 accumulation = splat(0.0);
         for (uint32_t k = 0; k < nl; k++) {
             size_t s = (size_t)ev * nl + k;
-            uint2 hid = P.sh_id[s];
-            if (hid.x == LEAF_NONE) continue;
-            Hit h;
-            h.t = P.sh_t[s]; h.u = P.sh_u[s]; h.v = P.sh_v[s]; h.kind = hid.x; h.id = hid.y;
+            const uint32_t slot = P.cap + (uint32_t)s;  // the shadow rays' lists follow the camera rays'
+            const uint32_t cn = __ldcs(cand.n + slot);
+            if (cn == 0u || cn == CAND_OCCLUDED) continue;  // nothing near the light sample, or something in front of it
+            const float ub = __ldcs(cand.ub + slot);
+            const uint32_t cid0 = __ldcs(cand.id + slot);
+            const float lo0 = __ldcs(cand.lo + slot);
             D3 o = d3(P.sray[0][s], P.sray[1][s], P.sray[2][s]);
             D3 d = d3(P.sray[3][s], P.sray[4][s], P.sray[5][s]);
+            const Hit h = confirm_ray<STATS>(sc, cand, slot, cn, ub, cid0, lo0, o, d, n_prims);
+            if (h.kind == LEAF_NONE) continue;
             D3 s_position = d3(P.s_pos[0][s], P.s_pos[1][s], P.s_pos[2][s]);
             D3 hit_pos = o + d * h.t;
             if (norm(hit_pos - s_position) < sc.offset * 4.0) {  // Vector3::approximately (src/vector.rs:89-91)
@@ -588,6 +595,10 @@ __global__ void __launch_bounds__(256) k_nee_resolve(RParams P, int bounce) {
         L = L + thr * nee;       // src/renderer.rs:183
         L = L + thr * emission;  // :196
         P.L[0][pid] = L.x; P.L[1][pid] = L.y; P.L[2][pid] = L.z;
+    }
+    if (STATS) {
+        for (int o = 16; o > 0; o >>= 1) n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&P.stats[S_PRIMS], (unsigned long long)n_prims);
     }
 }
 

@@ -402,7 +402,41 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     }
 }
 
+// The exact closest hit of one ray from its candidate list (or by the plain exact traversal if the list overflowed).
+// The header and entry 0 are passed in so that the caller can request them together with everything else it needs.
+template <bool STATS>
+HNM_D Hit confirm_ray(const DScene& sc, const CandLists& cand, uint32_t slot, uint32_t n, float ub, uint32_t cid0, float lo0, D3 o, D3 dir,
+                      uint32_t& n_prims) {
+    Hit best;
+    best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
+    if (n == CAND_OVERFLOW) {
+        TraceStats st{0, 0};
+        best = trace<STATS>(sc, o, dir, &st);
+        if (STATS) n_prims += st.prims;
+    } else if (n != CAND_OCCLUDED) {
+        for (uint32_t k = 0; k < n; k++) {
+            const size_t at = (size_t)k * cand.stride + slot;
+            const float lo = k == 0 ? lo0 : __ldcs(cand.lo + at);
+            if (lo > ub) continue;  // culled after it was listed
+            const uint32_t cid = k == 0 ? cid0 : __ldcs(cand.id + at);
+            const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
+            if (STATS) n_prims++;
+            if (kind == LEAF_TRI) {
+                DTri tr = load_tri(sc.tris + id);
+                tri_test(tr, id, o, dir, best);
+            } else if (kind == LEAF_SPHERE) {
+                sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
+            } else {
+                cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
+            }
+        }
+    }
+    return best;
+}
+
 // Exact closest hit of every ray from its candidate list; hit records; shading queues for job 0.
+// (The NEE shadow rays of the path tracer are confirmed inside k_nee_resolve instead: their hit is consumed there
+// and nowhere else.)
 template <bool STATS>
 __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene sc, TraceArgs A) {
     const int lane = threadIdx.x & 31;
@@ -428,30 +462,7 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
             const float lo0 = __ldcs(A.cand.lo + slot);
             const D3 o = d3(__ldcs(J.ray[0] + q), __ldcs(J.ray[1] + q), __ldcs(J.ray[2] + q));
             const D3 dir = d3(__ldcs(J.ray[3] + q), __ldcs(J.ray[4] + q), __ldcs(J.ray[5] + q));
-            Hit best;
-            best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
-            if (n == CAND_OVERFLOW) {
-                TraceStats st{0, 0};
-                best = trace<STATS>(sc, o, dir, &st);
-                if (STATS) n_prims += st.prims;
-            } else if (n != CAND_OCCLUDED) {
-                for (uint32_t k = 0; k < n; k++) {
-                    const size_t at = (size_t)k * A.cand.stride + slot;
-                    const float lo = k == 0 ? lo0 : __ldcs(A.cand.lo + at);
-                    if (lo > ub) continue;  // culled after it was listed
-                    const uint32_t cid = k == 0 ? cid0 : __ldcs(A.cand.id + at);
-                    const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
-                    if (STATS) n_prims++;
-                    if (kind == LEAF_TRI) {
-                        DTri tr = load_tri(sc.tris + id);
-                        tri_test(tr, id, o, dir, best);
-                    } else if (kind == LEAF_SPHERE) {
-                        sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
-                    } else {
-                        cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
-                    }
-                }
-            }
+            const Hit best = confirm_ray<STATS>(sc, A.cand, slot, n, ub, cid0, lo0, o, dir, n_prims);
             __stcs(J.hit_t + q, best.t); __stcs(J.hit_u + q, best.u); __stcs(J.hit_v + q, best.v);
             __stcs(J.hit_id + q, make_uint2(best.kind, best.id));
             if (!j1 && classify) {
