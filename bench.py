@@ -372,6 +372,12 @@ def main():
         g.build_host()
         g.build_core()
         g.build_oracle()
+    else:
+        # rank 0 builds (a no-op when the in-tree libraries are current; the swap is atomic); the others only need the files to exist
+        libs = [os.path.join(ROOT, "hanamaru_renderer_b200", n) for n in ("libhanamaru_host.so", "libhanamaru_b200.so")]
+        t0 = time.time()
+        while not all(os.path.exists(p) for p in libs) and time.time() - t0 < 600:
+            time.sleep(1.0)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
