@@ -38,6 +38,9 @@ namespace hnm {
 #define HNM_TRACE_LEAF_STEPS 2  /* max leaf steps per scheduling vote */
 #endif
 
+#ifndef HNM_TRACE_FMA_SLABS
+#define HNM_TRACE_FMA_SLABS 1
+#endif
 #ifndef HNM_CONFIRM_MIN_BLOCKS
 #define HNM_CONFIRM_MIN_BLOCKS 3
 #endif
@@ -97,6 +100,11 @@ struct RayF {
     float rx, ry, rz;      // -direction
     float K;               // absolute error bound of (origin - vertex) in f32
     float t0;              // distance the origin was advanced by (>= true value), 0 normally
+#if HNM_TRACE_FMA_SLABS
+    // node slab tests as one fma per plane: t = plane * inv + c with c = -(origin * inv), widened by the rounding of
+    // that product (2^-22 relative to |origin * inv|) towards -inf for the entry planes and +inf for the exit planes
+    float nx, ny, nz, fx, fy, fz;
+#endif
 };
 
 // Conservative f32 triangle pre-test.  Returns false only if the exact test (src/bvh.rs:266-290) cannot accept
@@ -219,6 +227,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     uint32_t slot = 0;       // this ray's candidate list
     RayF R;
     R.ox = R.oy = R.oz = R.ix = R.iy = R.iz = R.rx = R.ry = R.rz = 0.f; R.K = 0.f; R.t0 = 0.f;
+#if HNM_TRACE_FMA_SLABS
+    R.nx = R.ny = R.nz = R.fx = R.fy = R.fz = 0.f;
+#endif
     float best_ub = 3.0e38f;
     float t_occ = -3.0e38f;  // shadow rays: a certain hit closer than this ends the ray (see TraceJob::tmax)
     uint32_t ncand = 0;
@@ -288,6 +299,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         R.t0 = __double2float_ru(t0);
                         // |f32(origin) - origin| + |f32(vertex) - vertex| + rounding of the difference, with 4x slack
                         R.K = (fmaxf(fmaxf(fabsf(R.ox), fabsf(R.oy)), fabsf(R.oz)) + sc.scene_r) * 4.76837158203125e-07f;
+#if HNM_TRACE_FMA_SLABS
+                        {
+                            const float E = 2.384185791015625e-07f;  // 2^-22
+                            const float cx = R.ox * R.ix, cy = R.oy * R.iy, cz = R.oz * R.iz;
+                            R.nx = -cx - fabsf(cx) * E; R.ny = -cy - fabsf(cy) * E; R.nz = -cz - fabsf(cz) * E;
+                            R.fx = -cx + fabsf(cx) * E; R.fy = -cy + fabsf(cy) * E; R.fz = -cz + fabsf(cz) * E;
+                        }
+#endif
                     }
                 }
                 more = more && base + (uint32_t)__popc(need) < ntot;
@@ -318,6 +337,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         int2 m3 = __ldg(reinterpret_cast<const int2*>(np + 3));
                         if (STATS) n_nodes++;
 
+#if HNM_TRACE_FMA_SLABS
+                        // entry / exit plane per axis by the sign of the direction, one fma per plane (12 instead of 24
+                        // operations per node; a NaN -- axis-parallel ray -- drops out of the min / max: conservative)
+                        const bool px = R.ix >= 0.0f, py = R.iy >= 0.0f, pz = R.iz >= 0.0f;
+                        // child 0: lo = (m0.x m0.y m0.z) hi = (m0.w m1.x m1.y); child 1: lo = (m1.z m1.w m2.x) hi = (m2.y m2.z m2.w)
+                        float tmin0 = fmaxf(fmaxf(__fmaf_rn(px ? m0.x : m0.w, R.ix, R.nx), __fmaf_rn(py ? m0.y : m1.x, R.iy, R.ny)),
+                                            __fmaf_rn(pz ? m0.z : m1.y, R.iz, R.nz));
+                        float tmax0 = fminf(fminf(__fmaf_rn(px ? m0.w : m0.x, R.ix, R.fx), __fmaf_rn(py ? m1.x : m0.y, R.iy, R.fy)),
+                                            __fmaf_rn(pz ? m1.y : m0.z, R.iz, R.fz));
+                        float tmin1 = fmaxf(fmaxf(__fmaf_rn(px ? m1.z : m2.y, R.ix, R.nx), __fmaf_rn(py ? m1.w : m2.z, R.iy, R.ny)),
+                                            __fmaf_rn(pz ? m2.x : m2.w, R.iz, R.nz));
+                        float tmax1 = fminf(fminf(__fmaf_rn(px ? m2.y : m1.z, R.ix, R.fx), __fmaf_rn(py ? m2.z : m1.w, R.iy, R.fy)),
+                                            __fmaf_rn(pz ? m2.w : m2.x, R.iz, R.fz));
+#else
                         float a0 = (m0.x - R.ox) * R.ix, b0 = (m0.w - R.ox) * R.ix;
                         float a1 = (m0.y - R.oy) * R.iy, b1 = (m1.x - R.oy) * R.iy;
                         float a2 = (m0.z - R.oz) * R.iz, b2 = (m1.y - R.oz) * R.iz;
@@ -328,6 +361,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         float g2 = (m2.x - R.oz) * R.iz, e2 = (m2.w - R.oz) * R.iz;
                         float tmin1 = fmaxf(fmaxf(fminf(g0, e0), fminf(g1, e1)), fminf(g2, e2));
                         float tmax1 = fminf(fminf(fmaxf(g0, e0), fmaxf(g1, e1)), fmaxf(g2, e2));
+#endif
                         // relative margin for the f32 roundings: widen towards 0 / +inf.  (For a negative bound the product
                         // moves the other way, by 2^-21 relative -- irrelevant: a box with tmax < 0 is behind the ray either
                         // way, and a negative tmin only ever meets the tests `<= up` and `<= best_ub` with non-negative right sides.)
