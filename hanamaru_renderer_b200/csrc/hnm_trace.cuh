@@ -137,11 +137,12 @@ HNM_D bool tri_pretest(const float4* __restrict__ tf, const RayF& R, float& best
     if (tn + Mt < -R.t0 * dhi) return false;              // t < 0 for sure (t is measured from the advanced origin)
     const float num_lo = tn - Mt;
     if (num_lo > best_ub * dhi) return false;             // t > best_ub for sure
-    *t_lo = num_lo > 0.0f ? (num_lo / dhi) * 0.99999976f : -3.0e38f;
+    // (approximate division, 2 ulp, widened by 2^-20: the quotient only has to be a bound)
+    *t_lo = num_lo > 0.0f ? __fdividef(num_lo, dhi) * 0.99999905f : -3.0e38f;
     const float dlo = aden - Mden;
     if (dlo > Mden && un >= Mu && vn >= Mv && un + vn <= dlo - (Mu + Mv) && num_lo >= 0.0f && R.t0 == 0.0f) {
         // inside by the full margin: the exact test accepts it at t <= (tn + Mt) / (aden - Mden)
-        float t_ub = ((tn + Mt) / dlo) * 1.0000005f;
+        float t_ub = __fdividef(tn + Mt, dlo) * 1.000001f;
         best_ub = fminf(best_ub, t_ub);
     }
     return true;
