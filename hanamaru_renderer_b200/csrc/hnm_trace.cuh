@@ -81,16 +81,6 @@ struct TraceArgs {
     float tmax_slack;               // half-width of the window around tmax[] inside which the exact closest hit matters
 };
 
-HNM_D void warp_queue_push(bool pred, uint32_t* counter, uint32_t* queue, uint32_t value, int lane) {
-    unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
-    if (mask == 0) return;
-    int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xFFFFFFFFu, base, leader);
-    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
-}
-
 HNM_D float l1(float x, float y, float z) { return fabsf(x) + fabsf(y) + fabsf(z); }
 
 // per-lane traversal state that the f32 phase reads
@@ -511,10 +501,23 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
             }
         }
         if (classify) {
+            // three queues, ONE round trip: lanes 0..2 each reserve the warp's slots in one queue at the same time
+            // (ncu, round 1: the three back-to-back atomics were 14 % of this kernel's stall samples)
             const TraceJob& J0 = A.job[0];
-            warp_queue_push(cls == 0, J0.cnt_miss, J0.q_miss, idx, lane);
-            warp_queue_push(cls == 1, J0.cnt_delta, J0.q_delta, idx, lane);
-            warp_queue_push(cls == 2, J0.cnt_nee, J0.q_nee, idx, lane);
+            const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == 0), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1),
+                           m2 = __ballot_sync(0xFFFFFFFFu, cls == 2);
+            uint32_t base = 0;
+            if (lane < 3) {
+                const unsigned m = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+                uint32_t* ctr = lane == 0 ? J0.cnt_miss : (lane == 1 ? J0.cnt_delta : J0.cnt_nee);
+                if (m) base = atomicAdd(ctr, (uint32_t)__popc(m));
+            }
+            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, base, 0), b1 = __shfl_sync(0xFFFFFFFFu, base, 1), b2 = __shfl_sync(0xFFFFFFFFu, base, 2);
+            if (cls >= 0) {
+                const unsigned m = cls == 0 ? m0 : (cls == 1 ? m1 : m2);
+                uint32_t* q = cls == 0 ? J0.q_miss : (cls == 1 ? J0.q_delta : J0.q_nee);
+                q[(cls == 0 ? b0 : (cls == 1 ? b1 : b2)) + __popc(m & ((1u << lane) - 1u))] = idx;
+            }
         }
     }
     if (STATS) {
