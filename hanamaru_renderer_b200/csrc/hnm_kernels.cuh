@@ -165,19 +165,25 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
     // latencies per step on the critical chain.  Here x and mem[ind(x)] of the NEXT step are loaded before this
     // step's store and the one possible alias (ind(x') == i) is patched by forwarding y: one latency per step.
     uint64_t aa = 0, bb = 1;
+    // data-dependent addresses with one operation less on the dependent chain: byte offset of mem[(x >> 3) & 255] is
+    // (x & 0x7f8) * T, that of mem[(y >> 11) & 255] is the high word of (y & 0x7f800) * ((8 * T) << 21)
+    static_assert(8 * T < 2048, "the umulhi form needs (8 * T) << 21 to fit 32 bits");
+    const char* const memb = reinterpret_cast<const char*>(mem);
+#define MEMX(x) (*reinterpret_cast<const uint64_t*>(memb + ((uint32_t)(x) & 0x7f8u) * (uint32_t)T))
+#define MEMY(y) (*reinterpret_cast<const uint64_t*>(memb + __umulhi((uint32_t)(y) & 0x7f800u, (uint32_t)(8 * T) << 21)))
     uint64_t xn = MEM(0);
-    uint64_t pn = MEM(((uint32_t)xn >> 3) & 255u);
+    uint64_t pn = MEMX(xn);
 #define ISAAC_STEP(mixexpr, i, i2, SINK)                             \
     {                                                               \
         const uint64_t x = xn, p = pn;                              \
         xn = MEM(((i) + 1) & 255);  /* i == 255: a dummy load */    \
         const uint32_t jn = ((uint32_t)xn >> 3) & 255u;             \
-        pn = MEM(jn);                                               \
+        pn = MEMX(xn);                                              \
         aa = (mixexpr) + MEM(i2);                                   \
         const uint64_t y = p + aa + bb;                             \
         MEM(i) = y;                                                 \
         if (jn == (uint32_t)(i)) pn = y;                            \
-        bb = MEM(((uint32_t)y >> 11) & 255u) + x;                   \
+        bb = MEMY(y) + x;                                           \
         SINK(i, bb);                                                \
     }
 #define ISAAC_NOSINK(i, v)
@@ -205,6 +211,8 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
     }
 #undef ISAAC_NOSINK
 #undef ISAAC_STEP
+#undef MEMX
+#undef MEMY
 #undef MEM
 }
 
