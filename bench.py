@@ -129,6 +129,9 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0  # rank 0 alone runs the CPU arm
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads (it is the only
+    # process doing work), so undo that before the OpenMP runtime of the oracle library initialises
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import hanamaru_renderer_b200 as hr
     from oracle_ffi import Oracle  # the one other place bench.py may execute oracle/
