@@ -501,13 +501,19 @@ int hnm_render_passes(hnm_renderer* r, uint32_t sampling_first, uint32_t count) 
     if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
     if (r->P.mode != HNM_MODE_PATHTRACING && count > 1) count = 1;  // DebugRenderer::max_sampling() == 1
     HNM_CUDA(cudaSetDevice(r->scene->device));
+    // The call is cut into ceil(count / max_batch) batches of (nearly) EQUAL size -- 16 passes with room for 3 in flight
+    // run as 3 3 3 3 2 2, not 3 3 3 3 3 1: a thin last batch wastes the machine.  The batch after each one is known
+    // inside the call; across calls it is guessed as the first batch of an identical call that continues the pass
+    // numbering (`sampling` only ever counts up, src/renderer.rs:32).  A wrong guess costs one discarded generation.
+    auto batch_size = [&](uint32_t remaining) {
+        uint32_t nb = (remaining + r->max_batch - 1) / r->max_batch;
+        return (remaining + nb - 1) / nb;
+    };
     uint32_t done = 0;
     while (done < count) {
-        uint32_t b = std::min(r->max_batch, count - done);
-        // the batch after this one: the rest of this call, else (speculatively) the pass loop's next call --
-        // `sampling` only ever counts up by one (src/renderer.rs:32); a wrong guess costs one discarded generation
-        uint32_t left = count - done - b;
-        uint32_t nb = left > 0 ? std::min(r->max_batch, left) : (r->speculate ? b : 0u);
+        const uint32_t b = batch_size(count - done);
+        const uint32_t left = count - done - b;
+        const uint32_t nb = left > 0 ? batch_size(left) : (r->speculate ? batch_size(count) : 0u);
         int rc = run_batch(r, sampling_first + done, b, sampling_first + done + b, nb);
         if (rc) return rc;
         done += b;
