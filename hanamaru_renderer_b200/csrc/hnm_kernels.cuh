@@ -1,14 +1,18 @@
-// hnm_kernels.cuh -- the wavefront kernel set around k_trace (hnm_trace.cuh).
+// hnm_kernels.cuh -- the wavefront kernel set around k_trace / k_confirm (hnm_trace.cuh).
 //
 // One batch of passes of PathTracingRenderer (src/renderer.rs:148-203):
 //   k_isaac_raygen   ISAAC-64 seeding per path (rand 0.4 StdRng; 2 KB of state per path in shared memory,
-//                    112 paths per CTA) + thin-lens camera ray (src/camera.rs:66-96)
+//                    112 paths per CTA) + thin-lens camera ray (src/camera.rs:66-96); runs on the renderer's RNG
+//                    stream, one batch ahead of the kernels below (hanamaru_b200.cu: GenSet)
 //   k_rng_overflow   exact slow path for the (rare) paths whose lens rejection loop outruns the stored
 //                    tail of the random stream
+//   k_batch_begin    hands the generated batch to the renderer's stream (ray count, path / fallback statistics)
 //   per bounce b = 1 .. bounce_limit-1:
-//     k_trace        job 0: camera-path rays of bounce b (hits classified into miss / delta / NEE queues)
-//                    job 1: the NEE shadow rays of bounce b-1
-//     k_nee_resolve  (b-1) visibility test + light contribution (src/renderer.rs:282-291), radiance update
+//     k_trace        f32 candidate search; job 0: camera-path rays of bounce b, job 1: the NEE shadow rays of bounce b-1
+//     k_confirm      exact closest hit of the camera rays from their candidate lists, classified into the
+//                    miss / delta-BSDF / NEE-BSDF queues
+//     k_nee_resolve  (b-1) exact closest hit of the shadow rays, visibility test + light contribution
+//                    (src/renderer.rs:282-291), radiance update
 //     k_shade_miss   Skybox::sample (src/scene.rs:295-319), radiance update, path ends
 //     k_shade_surf   material resolve, BSDF sample, throughput update, compaction into the next ray queue;
 //                    Diffuse / GGX hits also emit one shadow ray per emitter (src/renderer.rs:269-281)
