@@ -224,7 +224,13 @@ void hnm_renderer_destroy(hnm_renderer* r);
 /* Runs passes sampling_first .. sampling_first+count-1 of the pass loop
  * (src/renderer.rs:32-38; `sampling` is 1-origin and is part of every path's
  * RNG seed, src/renderer.rs:167) and adds them to the accumulation buffer in
- * pass order.  Asynchronous: returns once the work is enqueued. */
+ * pass order.  Asynchronous: returns once the work is enqueued.
+ * The call is cut into equal-sized batches of at most `max_batch` passes.  The
+ * random streams and camera rays of the batch after the current one are
+ * generated ahead of time on a second stream; after the last batch of a call
+ * that is a guess (an identical call continuing the pass numbering, which is
+ * what the reference's pass loop does).  A wrong guess is discarded: results
+ * never depend on it.  HNM_RNG_OVERLAP=0 / HNM_RNG_SPECULATE=0 switch it off. */
 int hnm_render_passes(hnm_renderer* r, uint32_t sampling_first, uint32_t count);
 int hnm_synchronize(hnm_renderer* r);
 int hnm_clear(hnm_renderer* r);
