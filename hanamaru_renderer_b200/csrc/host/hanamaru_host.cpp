@@ -820,6 +820,45 @@ static SceneAndCamera scene_tbf3(const AssetStore& a, const std::string& sky) {
 }
 SceneAndCamera init_scene_tbf3(const AssetStore& a) { return scene_tbf3(a, "textures/cube/LancellottiChapel"); }
 
+// src/main.rs:725-802
+static SceneAndCamera scene_rtcamp6_v1(const AssetStore& a, const std::string& sky) {
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 2.0, 10.0), Vector3(0.0, 1.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 10.0, LensShape::Circle, 0.2 * 0.0, 8.8);
+    double radius = 0.6;
+    Scene& scene = sc.scene;
+    scene.add(std::make_unique<Sphere>(Vector3(0.0, 3.1782 * 0.4, 0.0), radius,
+                                       Material{SurfaceType::Diffuse(), Texture::white(), Texture::from_color(Color::from_one(10.0)), Texture::from_color(Color::from_one(0.05))}));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/houdini_boss.obj", Matrix44::scale_linear(0.4) * Matrix44::translate(0.0, 3.1782, 2.0) * Matrix44::rotate_y(-0.5),
+        Material{SurfaceType::Refraction(1.5), Texture::from_color(Color(0.7, 0.7, 1.0)), Texture::black(), Texture::from_color(Color::from_one(0.1))})));
+    scene.add(std::make_unique<Cuboid>(Aabb{Vector3(-5.0, -1.0, -5.0), Vector3(5.0, 0.0, 5.0)},
+                                       Material{SurfaceType::Diffuse(), tex_path(a, "textures/2d/checkered_diagonal_10_0.5_1.0_512.png"), Texture::black(),
+                                                tex_path(a, "textures/2d/checkered_diagonal_10_0.1_0.6_512.png")}));
+    scene.skybox = make_skybox(a, sky, Vector3::from_one(0.5));
+    return sc;
+}
+SceneAndCamera init_scene_rtcamp6_v1(const AssetStore& a) { return scene_rtcamp6_v1(a, "textures/cube/LancellottiChapel"); }
+
+// src/main.rs:928-1018: the second emitter is a 1 mm sphere one unit BEHIND the camera (smaller than the 0.02 window
+// of the NEE visibility test)
+SceneAndCamera init_scene_rtcamp6_v3(const AssetStore& a) {
+    SceneAndCamera sc;
+    sc.camera = Camera(Vector3(0.0, 2.0, 6.0), Vector3(0.0, 1.0, 0.0), Vector3(0.0, 1.0, 0.0).normalize(), 20.0, LensShape::Circle, 0.2, 4.9);
+    double radius = 0.2;
+    Scene& scene = sc.scene;
+    scene.add(std::make_unique<Sphere>(Vector3(-0.3, 0.5 + radius, 0.0), radius,
+                                       Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color::from_one(10.0)), Texture::black()}));
+    scene.add(std::make_unique<Sphere>(sc.camera.eye - sc.camera.forward, 0.001,
+                                       Material{SurfaceType::Diffuse(), Texture::black(), Texture::from_color(Color::from_one(1000.0)), Texture::black()}));
+    scene.add(BvhMesh::from_mesh(ObjLoader::load(
+        a, "models/bunny/bunny_wired_300.obj", Matrix44::scale_linear(1.5) * Matrix44::translate(0.0, 0.0, 0.0) * Matrix44::rotate_y(0.3),
+        Material{SurfaceType::GGX(0.8), Texture::from_color(Color(1.0, 0.01, 0.01)), Texture::black(), Texture::from_color(Color::from_one(0.05))})));
+    scene.add(std::make_unique<Cuboid>(Aabb{Vector3(-5.0, -1.0, -5.0), Vector3(5.0, 0.0, 5.0)},
+                                       Material{SurfaceType::Diffuse(), Texture::white(), Texture::black(), Texture::white()}));
+    scene.skybox = make_skybox(a, "textures/cube/Powerlines", Vector3::from_one(1.0));
+    return sc;
+}
+
 // src/main.rs:804-925: 100 GGX spheres and FIVE emissive ones placed by StdRng (five shadow rays per NEE event)
 // around a refractive fractal
 static SceneAndCamera scene_rtcamp6_v2(const AssetStore& a, const std::string& sky) {
@@ -907,6 +946,9 @@ SceneAndCamera init_scene_by_name(const std::string& name, const AssetStore& a) 
     // the same two scenes under the (much smaller) Powerlines cubemap, so that they fit the committed asset pack
     if (name == "simple_pl") return scene_simple(a, "textures/cube/Powerlines");
     if (name == "material_examples_pl") return scene_material_examples(a, "textures/cube/Powerlines");
+    if (name == "rtcamp6_v1") return init_scene_rtcamp6_v1(a);
+    if (name == "rtcamp6_v1_pl") return scene_rtcamp6_v1(a, "textures/cube/Powerlines");
+    if (name == "rtcamp6_v3") return init_scene_rtcamp6_v3(a);
     if (name == "rtcamp6_v2") return init_scene_rtcamp6_v2(a);
     if (name == "rtcamp6_v2_pl") return scene_rtcamp6_v2(a, "textures/cube/Powerlines");
     if (name == "rtcamp5") return init_scene_rtcamp5(a);
@@ -928,7 +970,12 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
     if (images) {
         if (rt || name == "diamond") { add(cube("textures/cube/Powerlines")); out.push_back("textures/2d/magic-circle3.png"); }
         if (name == "rtcamp6_v4" || name == "rtcamp6_v2") add(cube("textures/cube/Ryfjallet"));
-        if (name == "rtcamp6_v2_pl") add(cube("textures/cube/Powerlines"));
+        if (name == "rtcamp6_v2_pl" || name == "rtcamp6_v3") add(cube("textures/cube/Powerlines"));
+        if (name == "rtcamp6_v1" || name == "rtcamp6_v1_pl") {
+            add(cube(name == "rtcamp6_v1" ? "textures/cube/LancellottiChapel" : "textures/cube/Powerlines"));
+            out.push_back("textures/2d/checkered_diagonal_10_0.5_1.0_512.png");
+            out.push_back("textures/2d/checkered_diagonal_10_0.1_0.6_512.png");
+        }
         if (name == "rtcamp5" || name == "tbf3" || name == "rtcamp5_pl" || name == "tbf3_pl") {
             add(cube(name.size() > 3 && name.substr(name.size() - 3) == "_pl" ? "textures/cube/Powerlines" : "textures/cube/LancellottiChapel"));
             add({EARTH, MARBLE_DIFFUSE, MARBLE_ROUGHNESS});
@@ -943,6 +990,8 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
         if (name == "bvh_heavy") add({"models/fractal_icosahedron.obj", "models/fractal_dodecahedron.obj"});
         if (name == "rtcamp6_v4") out.push_back("models/fractal_icosahedron.obj");
         if (name == "rtcamp6_v2" || name == "rtcamp6_v2_pl") out.push_back("models/fractal_dodecahedron.obj");
+        if (name == "rtcamp6_v1" || name == "rtcamp6_v1_pl") out.push_back("models/houdini_boss.obj");
+        if (name == "rtcamp6_v3") out.push_back("models/bunny/bunny_wired_300.obj");
         if (name == "diamond") out.push_back("models/round_brilliant.obj");
         if (name == "rtcamp5" || name == "rtcamp5_pl") add({"models/bunny/bunny_face1000.obj", "models/bunny/bunny_face1000_flip.obj", "models/dia/dia.obj"});
         if (name == "tbf3" || name == "tbf3_pl") add({"models/klab_logo/klab_logo_triangle.obj", "models/dia/dia.obj"});

@@ -301,6 +301,8 @@ SceneAndCamera init_scene_rtcamp6_v3_1(const AssetStore& a);  // src/main.rs:102
 SceneAndCamera init_scene_rtcamp6_v4(const AssetStore& a);    // src/main.rs:1155-1212
 SceneAndCamera init_scene_simple(const AssetStore& a);        // src/main.rs:54-131
 SceneAndCamera init_scene_material_examples(const AssetStore& a);  // src/main.rs:133-250
+SceneAndCamera init_scene_rtcamp6_v1(const AssetStore& a);    // src/main.rs:725-802
+SceneAndCamera init_scene_rtcamp6_v3(const AssetStore& a);    // src/main.rs:928-1018 (1 mm emitter behind the camera)
 SceneAndCamera init_scene_rtcamp6_v2(const AssetStore& a);    // src/main.rs:804-925 (105 StdRng-placed spheres, five emitters)
 SceneAndCamera init_scene_rtcamp5(const AssetStore& a);       // src/main.rs:252-499 (45 diamonds placed by StdRng)
 SceneAndCamera init_scene_tbf3(const AssetStore& a);          // src/main.rs:502-722 (four textured emitters)

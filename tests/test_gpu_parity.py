@@ -108,7 +108,7 @@ def _random_rays(rng, scene, n):
     return o, d
 
 
-@pytest.mark.parametrize("name", ["rtcamp6", "bvh_heavy", "diamond", "material_examples_pl", "simple_pl", "tbf3_pl", "rtcamp5_pl", "rtcamp6_v2_pl"])
+@pytest.mark.parametrize("name", ["rtcamp6", "bvh_heavy", "diamond", "material_examples_pl", "simple_pl", "tbf3_pl", "rtcamp5_pl", "rtcamp6_v2_pl", "rtcamp6_v3"])
 def test_intersect_batch_matches_oracle(hr, core, oracle, get_scene, get_device_scene, name):
     """BvhScene::intersect incl. material resolve (textures, skybox) on random rays: every field bit-identical."""
     scene, dev = get_scene(name), get_device_scene(name)
@@ -280,6 +280,8 @@ def test_pathtracing_config1_bit_exact(hr, core, oracle, get_scene, get_device_s
     ("tbf3_pl", 160, 90, 1, 3),                 # four emitters with a TEXTURED emission (4 shadow rays per NEE), StdRng layout
     ("rtcamp5_pl", 160, 90, 1, 2),              # 45 diamonds (Refraction 2.42), textured emitter, roughness map, marble floor
     ("rtcamp6_v2_pl", 160, 90, 1, 2),           # 105 StdRng-placed spheres, FIVE emitters (5 shadow rays per NEE), no floor
+    ("rtcamp6_v3", 160, 90, 1, 2),              # second emitter: a 1 mm sphere behind the camera, smaller than the NEE window
+    ("rtcamp6_v1_pl", 160, 90, 1, 2),           # refractive mesh in front of the light, textured albedo AND roughness floor
     ("rtcamp6", 97, 61, 3, 2),                  # odd sizes
     ("rtcamp6", 1, 1, 1, 1),
     ("rtcamp6", 3, 200, 1, 1),                  # W < H: min(res) picks the width

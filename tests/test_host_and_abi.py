@@ -143,6 +143,13 @@ def test_rng_authored_scenes(hr, get_scene):
                 lo_i, hi_i = boxes[i]
                 lo_j, hi_j = boxes[j]
                 assert not ((lo_i < hi_j).all() and (hi_i > lo_j).all()), (i, j)
+    v3 = get_scene("rtcamp6_v3")
+    d3 = v3.desc.contents
+    cam = v3.camera.contents
+    assert v3.counts()["emissions"] == 2 and d3.elements[1].radius == 0.001
+    # the camera light sits at eye - forward (src/main.rs:957)
+    assert np.allclose(d3.elements[1].a.tuple(), np.array(cam.eye.tuple()) - np.array(cam.forward.tuple()), rtol=0, atol=1e-15)
+    assert get_scene("rtcamp6_v1_pl").counts() == {"elements": 3, "triangles": 2520, "mesh_nodes": 1023, "top_nodes": 1, "images": 8, "emissions": 1}
     v2 = get_scene("rtcamp6_v2_pl")
     assert v2.counts()["elements"] == 100 + 5 + 1 and v2.counts()["emissions"] == 5
     assert v2.desc.contents.skybox_intensity.tuple() == (0.5, 0.5, 0.5)

@@ -36,6 +36,7 @@ MESHES = [
     "models/bunny/bunny_face1000_flip.obj",
     "models/dia/dia.obj",
     "models/klab_logo/klab_logo_triangle.obj",
+    "models/houdini_boss.obj",
 ]
 IMAGES = [
     "textures/2d/magic-circle3.png",
