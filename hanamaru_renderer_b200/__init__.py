@@ -183,6 +183,14 @@ class SceneBuilder:
 
 
 # --------------------------------------------------------------------------- device side (C ABI)
+def device_count_or_zero():
+    """device_count() that answers 0 instead of raising when there is no driver / device (tests)."""
+    try:
+        return device_count()
+    except HanamaruError:
+        return 0
+
+
 def device_count():
     n = _ffi.core().hnm_device_count()
     return max(n, 0)
@@ -405,6 +413,18 @@ class PathTracingRenderer(Renderer):
         self.last_report_progress = now
         del done
         return False
+
+
+def host_render(scene, mode, width, height, sampling=1, time_limit_sec=1e9, report_interval_sec=1e9, passes_per_call=0, device=0):
+    """The reference-facing call through the C++ host mirror (csrc/host: `PathTracingRenderer` / `DebugRenderer` ::render
+    over the C ABI), the way a compiled host would drive the core.  Returns (uint8 image [H][W][3], passes done)."""
+    img = np.zeros((height, width, 3), np.uint8)
+    done = C.c_uint32(0)
+    rc = _ffi.host().hnmh_render(scene._h, int(mode), width, height, sampling, float(time_limit_sec), float(report_interval_sec),
+                                 passes_per_call, device, _vp(img), C.byref(done))
+    if rc != 0:
+        raise HanamaruError(_ffi.host().hnmh_last_error().decode())
+    return img, done.value
 
 
 # --------------------------------------------------------------------------- batch entry points

@@ -158,6 +158,7 @@ HOST_SYMBOLS = {
     "hnmh_scene_desc": (C.POINTER(SceneDesc), [_P]),
     "hnmh_scene_camera": (C.POINTER(Camera), [_P]),
     "hnmh_scene_destroy": (None, [_P]),
+    "hnmh_render": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_int, _P, C.POINTER(C.c_uint32)]),
     "hnmh_stdrng": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_double, C.c_double, _P]),
     "hnmh_builder_create": (_P, []),
     "hnmh_builder_destroy": (None, [_P]),

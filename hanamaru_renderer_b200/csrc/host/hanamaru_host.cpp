@@ -3,9 +3,12 @@
 // the hot path and nothing here touches CUDA.
 #include "hanamaru_host.h"
 
+#include <dlfcn.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -997,6 +1000,127 @@ std::vector<std::string> scene_asset_paths(const std::string& name, bool images)
         if (name == "tbf3" || name == "tbf3_pl") add({"models/klab_logo/klab_logo_triangle.obj", "models/dia/dia.obj"});
     }
     return out;
+}
+
+
+// ---- Renderer trait over the C ABI (src/renderer.rs:20-267) ---------------------------------------------
+// The CUDA core is resolved at run time: this library has no CUDA dependency, and there is no CPU fallback --
+// without libhanamaru_b200.so or a device, render() fails with a message.
+struct CoreApi {
+    void* lib = nullptr;
+    const char* (*last_error)(void) = nullptr;
+    int (*device_count)(void) = nullptr;
+    int (*scene_create)(const hnm_scene_desc*, int, hnm_scene**) = nullptr;
+    void (*scene_destroy)(hnm_scene*) = nullptr;
+    int (*renderer_create)(hnm_scene*, const hnm_camera*, uint32_t, uint32_t, int, const hnm_shard*, uint32_t, hnm_renderer**) = nullptr;
+    void (*renderer_destroy)(hnm_renderer*) = nullptr;
+    int (*render_passes)(hnm_renderer*, uint32_t, uint32_t) = nullptr;
+    int (*synchronize)(hnm_renderer*) = nullptr;
+    int (*resolve)(hnm_renderer*, const void*, uint32_t, uint8_t*) = nullptr;
+};
+const CoreApi* core_api(std::string* err) {
+    static CoreApi api;
+    static bool tried = false;
+    static std::string load_error;
+    if (!tried) {
+        tried = true;
+        std::string path;
+        if (const char* e = getenv("HNM_CORE_LIB")) path = e;
+        if (path.empty()) {
+            Dl_info info;
+            if (dladdr((const void*)&core_api, &info) && info.dli_fname) {
+                std::string self = info.dli_fname;
+                size_t slash = self.find_last_of('/');
+                path = (slash == std::string::npos ? std::string(".") : self.substr(0, slash)) + "/libhanamaru_b200.so";
+            } else {
+                path = "libhanamaru_b200.so";
+            }
+        }
+        api.lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (!api.lib) {
+            load_error = std::string("cannot load the CUDA core (") + path + "): " + dlerror();
+        } else {
+            bool ok = true;
+            auto sym = [&](const char* name) { void* p = dlsym(api.lib, name); if (!p) { ok = false; load_error = std::string("missing symbol ") + name; } return p; };
+            api.last_error = (const char* (*)(void))sym("hnm_last_error");
+            api.device_count = (int (*)(void))sym("hnm_device_count");
+            api.scene_create = (int (*)(const hnm_scene_desc*, int, hnm_scene**))sym("hnm_scene_create");
+            api.scene_destroy = (void (*)(hnm_scene*))sym("hnm_scene_destroy");
+            api.renderer_create = (int (*)(hnm_scene*, const hnm_camera*, uint32_t, uint32_t, int, const hnm_shard*, uint32_t, hnm_renderer**))sym("hnm_renderer_create");
+            api.renderer_destroy = (void (*)(hnm_renderer*))sym("hnm_renderer_destroy");
+            api.render_passes = (int (*)(hnm_renderer*, uint32_t, uint32_t))sym("hnm_render_passes");
+            api.synchronize = (int (*)(hnm_renderer*))sym("hnm_synchronize");
+            api.resolve = (int (*)(hnm_renderer*, const void*, uint32_t, uint8_t*))sym("hnm_resolve");
+            if (!ok) { dlclose(api.lib); api.lib = nullptr; }
+        }
+    }
+    if (!api.lib) { if (err) *err = load_error; return nullptr; }
+    return &api;
+}
+
+static double now_sec() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+uint32_t Renderer::render(const BvhScene& scene, const Camera& camera, ImageBuffer& imgbuf) { return render(scene, camera.abi(), imgbuf); }
+
+// src/renderer.rs:25-46: the pass loop; `sampling` is 1-origin; report_progress after every call may stop it
+uint32_t Renderer::render(const BvhScene& scene, const hnm_camera& camera, ImageBuffer& imgbuf) {
+    error.clear();
+    const CoreApi* api = core_api(&error);
+    if (!api) return 0;
+    if (api->device_count() < 1) { error = std::string("no CUDA device: ") + api->last_error(); return 0; }
+    hnm_scene* ds = nullptr;
+    if (api->scene_create(&scene.flat.desc, device, &ds) != 0) { error = api->last_error(); return 0; }
+    if (api->renderer_create(ds, &camera, imgbuf.width, imgbuf.height, mode(), nullptr, 0, &r_) != 0) {
+        error = api->last_error();
+        api->scene_destroy(ds);
+        return 0;
+    }
+    uint32_t sampling = 0;
+    const uint32_t limit = max_sampling();
+    while (sampling < limit) {
+        uint32_t n = passes_per_call ? std::min(passes_per_call, limit - sampling) : 1u;
+        if (api->render_passes(r_, sampling + 1, n) != 0 || api->synchronize(r_) != 0) { error = api->last_error(); break; }
+        sampling += n;
+        if (report_progress(sampling, imgbuf)) break;
+    }
+    api->renderer_destroy(r_);
+    r_ = nullptr;
+    api->scene_destroy(ds);
+    return error.empty() ? sampling : 0;
+}
+void Renderer::update_imgbuf(uint32_t sampling, ImageBuffer& imgbuf) {
+    const CoreApi* api = core_api(nullptr);
+    if (api && r_ && api->resolve(r_, nullptr, sampling, imgbuf.rgb.data()) != 0) error = api->last_error();
+}
+bool DebugRenderer::report_progress(uint32_t sampling, ImageBuffer& imgbuf) {  // src/renderer.rs:141-145
+    update_imgbuf(sampling, imgbuf);
+    return true;
+}
+PathTracingRenderer::PathTracingRenderer(uint32_t sampling, double time_limit_sec, double report_interval_sec)
+    : sampling_(sampling), time_limit_sec_(time_limit_sec), report_interval_sec_(report_interval_sec) {
+    begin_ = last_report_progress_ = last_report_image_ = now_sec();
+}
+// src/renderer.rs:205-251: stop when the time limit would be exceeded by another call like the last one (x1.1) or when
+// max sampling is reached; refresh the image every report interval
+bool PathTracingRenderer::report_progress(uint32_t sampling, ImageBuffer& imgbuf) {
+    const double now = now_sec();
+    const double used = now - begin_;
+    const double from_last = now - last_report_progress_;
+    if (verbose)
+        fprintf(stderr, "rendering: %ux4 sampled (last %.3f sec). total: %.3f sec (%.2f %%).\n", sampling, from_last, used, used / time_limit_sec_ * 100.0);
+    if (used + from_last * 1.1 > time_limit_sec_ || sampling >= max_sampling()) {
+        update_imgbuf(sampling, imgbuf);
+        return true;
+    }
+    if (now - last_report_image_ >= report_interval_sec_) {
+        update_imgbuf(sampling, imgbuf);
+        report_image_counter_ += 1;
+        last_report_image_ = now;
+    }
+    last_report_progress_ = now;
+    return false;
 }
 
 }  // namespace hanamaru

@@ -330,6 +330,8 @@ class Renderer {
     virtual int mode() const = 0;
     // src/renderer.rs:25-46: pass loop on the device, report_progress per batch
     uint32_t render(const BvhScene& scene, const Camera& camera, ImageBuffer& imgbuf);
+    // the same with the camera already in ABI form (what hnmh_scene_camera hands out)
+    uint32_t render(const BvhScene& scene, const hnm_camera& camera, ImageBuffer& imgbuf);
     // src/renderer.rs:62 -- true = stop
     virtual bool report_progress(uint32_t sampling, ImageBuffer& imgbuf) = 0;
     int device = 0;

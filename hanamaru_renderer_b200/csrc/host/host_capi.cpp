@@ -119,6 +119,36 @@ static Material make_material(const AssetStore* a, const hnmh_material* m) {
     return out;
 }
 
+// The reference-facing call in C++: `renderer.render(&scene, &camera, &mut imgbuf)` (src/main.rs:1216) with the C++
+// Renderer classes of hanamaru_host.h over the CUDA core.  mode 0 = PathTracingRenderer(sampling, time_limit, interval),
+// 1..4 = DebugRenderer.  rgb8 = width * height * 3 bytes; *passes_done = the return value of render().
+int hnmh_render(void* scene_handle, int mode, uint32_t width, uint32_t height, uint32_t sampling, double time_limit_sec,
+                double report_interval_sec, uint32_t passes_per_call, int device, uint8_t* rgb8, uint32_t* passes_done) {
+    if (!scene_handle || !rgb8 || !passes_done) { g_err = "null argument"; return -1; }
+    HNMH_TRY
+    SceneHandle* h = (SceneHandle*)scene_handle;
+    ImageBuffer img(width, height);
+    uint32_t done = 0;
+    std::string err;
+    if (mode == HNM_MODE_PATHTRACING) {
+        PathTracingRenderer r(sampling, time_limit_sec, report_interval_sec);
+        r.device = device;
+        r.passes_per_call = passes_per_call;
+        done = r.render(*h->bvh_scene, h->camera, img);
+        err = r.error;
+    } else {
+        DebugRenderer r(mode);
+        r.device = device;
+        done = r.render(*h->bvh_scene, h->camera, img);
+        err = r.error;
+    }
+    if (!err.empty()) { g_err = err; return -1; }
+    memcpy(rgb8, img.rgb.data(), img.rgb.size());
+    *passes_done = done;
+    return 0;
+    HNMH_CATCH(-1)
+}
+
 // rand 0.4.3 StdRng as the scene builders use it: `count` u64 outputs (kind 0) or gen_range(low, high) f64 draws
 // (kind 1, written as doubles) after skipping `skip` outputs -- for the known-answer tests
 int hnmh_stdrng(const uint64_t* seed, uint32_t nseed, uint32_t skip, uint32_t count, int kind, double low, double high, void* out) {

@@ -406,6 +406,25 @@ def test_renderer_surface(hr, core, oracle, get_scene, get_device_scene):
     assert np.array_equal(img, oracle.resolve(scene.desc.contents.config, want, 1))
 
 
+def test_cpp_host_renderer_matches_oracle(hr, core, oracle, get_scene):
+    """`renderer.render(&scene, &camera, &mut imgbuf)` through the C++ host mirror (csrc/host: PathTracingRenderer and
+    DebugRenderer over the C ABI, dlopen of the core): same u8 image as the oracle, same pass count as the reference loop."""
+    scene = get_scene("rtcamp6")
+    w, h = 160, 90
+    img, done = hr.host_render(scene, hr.MODE_PATHTRACING, w, h, sampling=3)
+    want, _ = oracle.render(scene, w, h, hr.MODE_PATHTRACING, 1, 3, counters=False)
+    assert done == 3 and np.array_equal(img, oracle.resolve(scene.desc.contents.config, want, 3))
+    img, done = hr.host_render(scene, hr.MODE_PATHTRACING, w, h, sampling=5, passes_per_call=2)
+    want, _ = oracle.render(scene, w, h, hr.MODE_PATHTRACING, 1, 5, counters=False)
+    assert done == 5 and np.array_equal(img, oracle.resolve(scene.desc.contents.config, want, 5))
+    img, done = hr.host_render(scene, hr.MODE_DEBUG_NORMAL, w, h)
+    want, _ = oracle.render(scene, w, h, hr.MODE_DEBUG_NORMAL, 1, 1, counters=False)
+    assert done == 1 and np.array_equal(img, oracle.resolve(scene.desc.contents.config, want, 1))
+    # a time limit that is already over stops after the first call (src/renderer.rs:216-226)
+    img, done = hr.host_render(scene, hr.MODE_PATHTRACING, w, h, sampling=50, time_limit_sec=0.0)
+    assert done == 1
+
+
 def test_full_size_properties(hr, core, oracle, get_scene, get_device_scene):
     """BASELINE config 2 size (1920x1080): one full pass is bit-identical to the oracle (8.3 M paths), and
     the multi-pass run keeps the size-independent invariants: determinism, additivity over passes, counters."""

@@ -251,6 +251,14 @@ def test_no_cpu_fallback_without_device(hr):
                 assert not re.search(r"^\s*(import|from)\s+oracle", text, flags=re.M), f
 
 
+def test_cpp_host_renderer_needs_the_device(hr, get_scene):
+    """The C++ host mirror (csrc/host Renderer::render over the C ABI) has no CPU fallback either."""
+    if hr.device_count_or_zero() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(hr.HanamaruError, match="CUDA"):
+        hr.host_render(get_scene("rtcamp6"), hr.MODE_PATHTRACING, 32, 18, 1)
+
+
 def test_scene_validation_rejects_malformed(hr, get_scene):
     """hnm_scene_create validates before touching the device: malformed descriptions -> HNM_ERR_INVALID."""
     import copy
