@@ -79,6 +79,20 @@ def test_committed_vectors(oracle, oracle_glibc, get_scene, hr):
             assert np.array_equal(orc.resolve(cfg, a, 1), v["debug_%s_96x54_rgb8" % name]), (name, orc.flavor)
 
 
+@pytest.mark.parametrize("name,lights", [("tbf3_pl", 4), ("rtcamp6_v2_pl", 5), ("rtcamp6_v3", 2), ("rtcamp5_pl", 1)])
+def test_multi_light_scenes_both_flavours(oracle, oracle_glibc, get_scene, hr, name, lights):
+    """NEE loops over EVERY emissive sphere (src/renderer.rs:275): one shadow ray per light and NEE-able hit.  The glibc
+    and the deterministic-libm flavours take the same discrete decisions on these scenes too."""
+    scene = get_scene(name)
+    assert scene.counts()["emissions"] == lights
+    acc, cnt = oracle.render(scene, 48, 27, hr.MODE_PATHTRACING, 1, 1)
+    acc_g, cnt_g = oracle_glibc.render(scene, 48, 27, hr.MODE_PATHTRACING, 1, 1)
+    assert cnt == cnt_g and cnt["shadow_rays"] % lights == 0 and cnt["shadow_rays"] > 0
+    rel = np.linalg.norm(acc_g - acc, axis=2) / np.maximum(np.linalg.norm(acc, axis=2), 1e-300)
+    assert rel.max() < 1e-10
+    assert np.isfinite(acc).all() and (acc >= 0).all() and acc.max() > 0
+
+
 def test_golden_image_statistical(oracle, get_scene, hr):
     """The reference's only golden artefact: rtcamp6_1000x4spp.png.  16 passes at 480x270 against the
     4x4 box-downsampled golden (tools/make_golden.py).  Different sample count and a different JPEG decoder, so
