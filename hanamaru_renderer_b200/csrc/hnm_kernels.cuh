@@ -439,7 +439,13 @@ HNM_D Rand2 bounce_random(const RParams& P, uint32_t pid, int bounce) {
     return r;
 }
 
-__global__ void __launch_bounds__(256) k_shade_miss(RParams P, int bounce) {
+#ifndef HNM_MISS_MIN_BLOCKS
+#define HNM_MISS_MIN_BLOCKS 4  /* 64 registers: 0.68 ms where the unconstrained build varied 0.68-0.93 */
+#endif
+#ifndef HNM_NEER_MIN_BLOCKS
+#define HNM_NEER_MIN_BLOCKS 4  /* 64 registers: 0.70 -> 0.60 ms */
+#endif
+__global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams P, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_MISS];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         uint32_t q = P.q_miss[i];
@@ -563,7 +569,7 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
 // shadow rays: exact closest hit of every shadow ray (confirm_ray -- its only consumer is right here, so no hit record
 // goes through memory), visibility test, light contribution, radiance update.
 template <bool STATS>
-__global__ void __launch_bounds__(256) k_nee_resolve(RParams P, CandLists cand, int bounce) {
+__global__ void __launch_bounds__(256, HNM_NEER_MIN_BLOCKS) k_nee_resolve(RParams P, CandLists cand, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_EVENTS];
     const uint32_t nl = P.sc.num_emissions;
     const DScene& sc = P.sc;
