@@ -193,7 +193,9 @@ def device_count_or_zero():
 
 def device_count():
     n = _ffi.core().hnm_device_count()
-    return max(n, 0)
+    if n < 0:  # a driver error is not "no device"
+        raise HanamaruError("hanamaru_b200 error %d: %s" % (n, _ffi.core().hnm_last_error().decode()))
+    return n
 
 
 class DeviceScene:
@@ -225,6 +227,22 @@ class DeviceScene:
         hits = np.zeros(len(rays), dtype=HIT_DTYPE)
         _check(_ffi.core().hnm_intersect_batch(self._h, _vp(rays), len(rays), _vp(hits)))
         return hits
+
+
+    def texture_sample(self, image, tint, uv):
+        """`Texture::sample` (src/texture.rs:108-114) of scene image `image` (-1: constant) at n (u, v) pairs."""
+        uv = np.ascontiguousarray(uv, np.float64).reshape(-1, 2)
+        t = np.asarray(tint, np.float64)
+        out = np.empty((len(uv), 3), np.float64)
+        _check(_ffi.core().hnm_texture_sample_batch(self._h, int(image), _vp(t), _vp(uv), len(uv), _vp(out)))
+        return out
+
+    def skybox_sample(self, directions):
+        """`Skybox::sample` (src/scene.rs:295-319) for n directions."""
+        d = np.ascontiguousarray(directions, np.float64).reshape(-1, 3)
+        out = np.empty((len(d), 3), np.float64)
+        _check(_ffi.core().hnm_skybox_sample_batch(self._h, _vp(d), len(d), _vp(out)))
+        return out
 
 
 HIT_DTYPE = np.dtype([("position", np.float64, 3), ("normal", np.float64, 3), ("albedo", np.float64, 3), ("emission", np.float64, 3),
@@ -313,6 +331,86 @@ class RenderContext:
         n = C.c_uint32()
         _check(_ffi.core().hnm_get_kernel_times(self._h, 32, names, ms, launches, C.byref(n)))
         return {names[i].decode(): (ms[i], launches[i]) for i in range(n.value)}
+
+
+    # ---- one process per device: the NCCL gather behind the C ABI (hnm_dist_*)
+    def dist_init(self, unique_id, rank, num_ranks):
+        buf = (C.c_uint8 * _ffi.HNM_DIST_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(_ffi.core().hnm_dist_init(self._h, buf, rank, num_ranks))
+
+    def dist_resolve(self, sampling, out=None, want_image=True):
+        """Collective.  Ranks with want_image=False only take part in the gather (asynchronously) and return None."""
+        if not want_image:
+            _check(_ffi.core().hnm_dist_resolve(self._h, sampling, None))
+            return None
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.uint8)
+        _check(_ffi.core().hnm_dist_resolve(self._h, sampling, _vp(out)))
+        return out
+
+    def dist_read_accum(self, want=True):
+        if not want:
+            _check(_ffi.core().hnm_dist_read_accum(self._h, None))
+            return None
+        out = np.empty((self.height, self.width, 3), np.float64)
+        _check(_ffi.core().hnm_dist_read_accum(self._h, _vp(out)))
+        return out
+
+
+def dist_unique_id():
+    """Rank 0: the NCCL unique id the launcher distributes to every rank (hnm_dist_init)."""
+    buf = (C.c_uint8 * _ffi.HNM_DIST_ID_BYTES)()
+    _check(_ffi.core().hnm_dist_unique_id(buf))
+    return bytes(buf)
+
+
+class RenderGroup:
+    """hnm_group: ONE process driving N devices -- scene uploaded to each, interleaved row tiles, peer-copy gather to
+    device 0, update_imgbuf there.  What a single-process host (the Rust binary) calls instead of RenderContext."""
+
+    def __init__(self, host_scene, camera, width, height, mode=MODE_PATHTRACING, devices=(0,), tile_rows=0, max_batch=0):
+        self.width, self.height, self.mode = width, height, mode
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(_ffi.core().hnm_group_create(host_scene.desc, camera, width, height, mode, len(devices), devs, tile_rows, max_batch, C.byref(h)))
+        self._h = h
+        self._keep = host_scene
+
+    def close(self):
+        if self._h:
+            _ffi.core().hnm_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def render_passes(self, sampling_first, count):
+        _check(_ffi.core().hnm_group_render_passes(self._h, sampling_first, count))
+
+    def synchronize(self):
+        _check(_ffi.core().hnm_group_synchronize(self._h))
+
+    def clear(self):
+        _check(_ffi.core().hnm_group_clear(self._h))
+
+    def resolve(self, sampling, out=None):
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.uint8)
+        _check(_ffi.core().hnm_group_resolve(self._h, sampling, _vp(out)))
+        return out
+
+    def read_accum(self):
+        out = np.empty((self.height, self.width, 3), np.float64)
+        _check(_ffi.core().hnm_group_read_accum(self._h, _vp(out)))
+        return out
+
+    def counters(self):
+        c = _ffi.Counters()
+        _check(_ffi.core().hnm_group_get_counters(self._h, C.byref(c)))
+        return {k: getattr(c, k) for k, _ in c._fields_}
 
 
 # --------------------------------------------------------------------------- the reference's Renderer surface

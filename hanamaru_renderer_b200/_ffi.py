@@ -141,7 +141,25 @@ CORE_SYMBOLS = {
     "hnm_material_sample_batch": (C.c_int, [C.c_int, _P, C.c_uint32, _P]),
     "hnm_material_bsdf_batch": (C.c_int, [C.c_int, _P, C.c_uint32, _P]),
     "hnm_math_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, C.c_uint32, _P]),
+    "hnm_texture_sample_batch": (C.c_int, [_P, C.c_int32, _P, _P, C.c_uint32, _P]),
+    "hnm_skybox_sample_batch": (C.c_int, [_P, _P, C.c_uint32, _P]),
+    "hnm_group_create": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_int),
+                                   C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "hnm_group_destroy": (None, [_P]),
+    "hnm_group_size": (C.c_uint32, [_P]),
+    "hnm_group_member": (_P, [_P, C.c_uint32]),
+    "hnm_group_render_passes": (C.c_int, [_P, C.c_uint32, C.c_uint32]),
+    "hnm_group_synchronize": (C.c_int, [_P]),
+    "hnm_group_clear": (C.c_int, [_P]),
+    "hnm_group_resolve": (C.c_int, [_P, C.c_uint32, _P]),
+    "hnm_group_read_accum": (C.c_int, [_P, _P]),
+    "hnm_group_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
+    "hnm_dist_unique_id": (C.c_int, [_P]),
+    "hnm_dist_init": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    "hnm_dist_resolve": (C.c_int, [_P, C.c_uint32, _P]),
+    "hnm_dist_read_accum": (C.c_int, [_P, _P]),
 }
+HNM_DIST_ID_BYTES = 128
 
 HOST_SYMBOLS = {
     "hnmh_last_error": (C.c_char_p, []),

@@ -1,8 +1,11 @@
 // hanamaru_b200.cu -- host side of the C ABI of include/hanamaru_b200.h: renderer state, the
 // per-batch kernel sequence (hnm_kernels.cuh, hnm_trace.cuh), resolve, counters and timing.
 // Compile with -fmad=false (parity: the reference never contracts a*b+c).
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 #include <map>
 #include <string>
 #include <vector>
@@ -53,6 +56,7 @@ struct hnm_renderer {
     size_t cap = 0;
     double *tmp0 = nullptr, *tmp1 = nullptr;
     uint8_t* rgb8 = nullptr;
+    uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
     bool profiling = false, trace_stats = false, per_bounce_names = false;
     uint64_t launches = 0;
     KernelTimer timer;
@@ -81,11 +85,25 @@ struct hnm_renderer {
     uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
     CandLists cand = {};           // candidate lists of the rays in flight: camera rays [0, cap), shadow rays [cap, cap + scap)
-    // NEE accepts a shadow hit iff |hit - light sample|^2 < 4 * offset (src/vector.rs:89-91, src/renderer.rs:282):
-    // only hits within sqrt(4 * offset) of the sample's distance matter.  Slack covers that plus the f32 roundings.
+    // NEE accepts a shadow hit iff |hit - light sample|^2 < 4 * offset (`norm()` is the squared length,
+    // src/vector.rs:35-37,89-91; src/renderer.rs:282): only hits within sqrt(4 * offset) of the sample's distance
+    // matter.  Slack covers that plus the f32 roundings.
     float tmax_slack = 0.0f;
     int trace_blocks_per_sm = HNM_TRACE_MIN_BLOCKS;  // persistent CTAs per SM = what the register budget allows
     cudaEvent_t marks[16] = {};
+    // multi-GPU gather target (hnm_group_* on device 0 of the group, hnm_dist_* on every rank): the shards of all ranks,
+    // and the full image in row order
+    double* gathered = nullptr;
+    double* full = nullptr;
+    void* nccl_comm = nullptr;     // ncclComm_t of hnm_dist_init
+    uint32_t dist_rank = 0, dist_nranks = 0;
+};
+
+struct hnm_group {
+    std::vector<hnm_scene*> scenes;
+    std::vector<hnm_renderer*> rs;
+    std::vector<cudaEvent_t> copied;  // per member: its shard has arrived on device 0
+    uint32_t W = 0, H = 0;
 };
 
 namespace {
@@ -111,6 +129,19 @@ int dev_alloc(std::vector<void*>& allocs, T** out, size_t count) {
     *out = (T*)p;
     return 0;
 }
+
+// One device allocation for all wavefront buffers of a renderer (round 1 made ~80 cudaMalloc calls, 0.2-0.8 s of
+// hnm_renderer_create at N = 8): the layout function runs twice, first to measure, then to hand out addresses.
+struct Arena {
+    char* base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    void take(T** out, size_t count) {
+        const size_t bytes = (std::max<size_t>(count * sizeof(T), 16) + 255) & ~(size_t)255;
+        *out = base ? (T*)(base + off) : nullptr;
+        off += bytes;
+    }
+};
 
 // which of the two ray queues the next launches read (`in`) and write (`out`)
 void select_buffers(hnm_renderer* r, int in) {
@@ -314,6 +345,80 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
     return 0;
 }
 
+// scratch device buffers of the batch entry points: released on every return path
+struct TmpDev {
+    std::vector<void*> v;
+    ~TmpDev() { for (auto p : v) cudaFree(p); }
+    template <typename T>
+    int alloc(T** out, size_t bytes) {
+        void* p = nullptr;
+        HNM_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        v.push_back(p);
+        *out = (T*)p;
+        return 0;
+    }
+    template <typename T>
+    int upload(T** out, const void* host, size_t bytes) {
+        int rc = alloc(out, bytes);
+        if (rc) return rc;
+        HNM_CUDA(cudaMemcpy(*out, host, bytes, cudaMemcpyHostToDevice));
+        return 0;
+    }
+};
+static int device_sm_count(int device, int* n) {
+    HNM_CUDA(cudaDeviceGetAttribute(n, cudaDevAttrMultiProcessorCount, device));
+    return 0;
+}
+
+
+// the gather target of a sharded renderer, allocated on first use
+int ensure_gather_buffers(hnm_renderer* r) {
+    if (r->gathered && r->full) return 0;
+    const size_t shard = (size_t)r->padded_rows * r->P.W * 3;
+    double *g = nullptr, *f = nullptr;
+    cudaError_t e = cudaMalloc(&g, shard * r->P.nranks * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&f, (size_t)r->P.W * r->P.H * 3 * sizeof(double));
+    if (e != cudaSuccess) { cudaFree(g); cudaFree(f); return set_error(HNM_ERR_NOMEM, std::string("gather buffers: ") + cudaGetErrorString(e)); }
+    r->allocs.push_back(g); r->allocs.push_back(f);
+    r->gathered = g; r->full = f;
+    return 0;
+}
+
+// ---- NCCL, bound at run time (dlopen): a single-GPU user needs no libnccl, and inside a process that already
+// loaded one (torch bundles its own) the same instance is used.  Only what the one exchange step needs.
+struct NcclApi {
+    typedef struct { char internal[128]; } UniqueId;  // ncclUniqueId
+    int (*GetUniqueId)(UniqueId*) = nullptr;
+    int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+    std::string why;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* h = nullptr;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { api.why = "libnccl.so.2 not found"; return; }
+        api.GetUniqueId = (int (*)(NcclApi::UniqueId*))dlsym(h, "ncclGetUniqueId");
+        api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
+        api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+        api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+        api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString;
+        if (!api.ok) api.why = "libnccl lacks an expected symbol";
+    });
+    return api;
+}
+constexpr int NCCL_FLOAT64 = 8;  // ncclFloat64 / ncclDouble (nccl.h: ncclDataType_t)
+#define HNM_NCCL(call)                                                                                     \
+    do {                                                                                                   \
+        int e__ = (call);                                                                                  \
+        if (e__ != 0) return set_error(HNM_ERR_CUDA, std::string(#call) + ": " + nccl().GetErrorString(e__)); \
+    } while (0)
 }  // namespace
 
 extern "C" {
@@ -336,7 +441,9 @@ void hnm_renderer_destroy(hnm_renderer* r) {
     if (r->rng_stream) cudaStreamSynchronize(r->rng_stream);
     if (r->stream) cudaStreamSynchronize(r->stream);
     r->timer.collect();
+    if (r->nccl_comm && nccl().ok) nccl().CommDestroy(r->nccl_comm);
     for (auto p : r->allocs) cudaFree(p);
+    if (r->rgb8_host) cudaFreeHost(r->rgb8_host);
     for (auto e : r->marks) if (e) cudaEventDestroy(e);
     for (auto& g : r->gen) {
         if (g.ready) cudaEventDestroy(g.ready);
@@ -359,8 +466,11 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (sh.num_ranks == 0 || sh.rank >= sh.num_ranks || sh.tile_rows == 0) return set_error(HNM_ERR_INVALID, "bad shard");
     if (sh.num_ranks == 1) sh.tile_rows = height;  // one tile: local row == image row
     HNM_CUDA(cudaSetDevice(scene->device));
+    int sm_count = 0;
+    HNM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, scene->device));  // before `new`: nothing to release on failure
     hnm_renderer* r = new hnm_renderer();
     r->scene = scene;
+    r->sm_count = sm_count;
     RParams& P = r->P;
     memset(&P, 0, sizeof(P));
     P.sc = scene->d;
@@ -386,9 +496,8 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     // rows that exist are a prefix of the local rows (tiles are assigned in increasing order)
     P.real_rows = real_rows;
     P.npix = real_rows * width;
-    cudaDeviceProp prop;
-    HNM_CUDA(cudaGetDeviceProperties(&prop, scene->device));
-    r->sm_count = prop.multiProcessorCount;
+    // NEE accepts a shadow hit iff (hit - sample).norm() < 4 * OFFSET, and `norm` is the SQUARED length
+    // (src/vector.rs:35-37,89-91): the hit must lie within sqrt(4 * OFFSET) = 0.02 of the sample.
     r->tmax_slack = (float)(std::sqrt(4.0 * scene->config.offset) * 1.05 + 1e-5 * (double)scene->d.scene_r + 1e-6);
     if (const char* e = getenv("HNM_SHADOW_BOUNDED")) { if (atoi(e) == 0) r->tmax_slack = 3.0e38f; }  // A/B: unbounded closest hit
     size_t per_pass = (size_t)P.npix * P.spp;
@@ -416,24 +525,58 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         if (ce != cudaSuccess) { set_error(HNM_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(ce)); return bail(HNM_ERR_CUDA); }
     }
     size_t cap = r->cap;
-    auto& A = r->allocs;
-    for (int b = 0; b < 2; b++) {
-        for (int k = 0; k < 6; k++) if ((rc = dev_alloc(A, &r->ray_buf[b][k], cap))) return bail(rc);
-        for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &r->thr_buf[b][k], cap))) return bail(rc);
-        if ((rc = dev_alloc(A, &r->pid_buf[b], cap))) return bail(rc);
+    const size_t scap = cap * std::max<uint32_t>(scene->num_emissions, 1);
+    const size_t nl = cap + (mode == HNM_MODE_PATHTRACING ? scap : 0);
+    if (nl >= (1ull << 32)) { set_error(HNM_ERR_INVALID, "too many rays in flight for 32-bit list slots"); return bail(HNM_ERR_INVALID); }
+    r->cand.stride = (uint32_t)nl;
+    const size_t accum_n = (size_t)r->padded_rows * width * 3;
+    auto layout = [&](Arena& A) {
+        for (int b = 0; b < 2; b++) {
+            for (int k = 0; k < 6; k++) A.take(&r->ray_buf[b][k], cap);
+            for (int k = 0; k < 3; k++) A.take(&r->thr_buf[b][k], cap);
+            A.take(&r->pid_buf[b], cap);
+        }
+        for (int s = 0; s < r->num_gen; s++) {
+            hnm_renderer::GenSet& g = r->gen[s];
+            for (int k = 0; k < 3; k++) A.take(&g.L[k], cap);
+            A.take(&g.cursor, cap);
+            if (mode == HNM_MODE_PATHTRACING) {
+                for (int k = 0; k < 6; k++) A.take(&g.ray[k], cap);
+                for (int k = 0; k < 3; k++) A.take(&g.thr[k], cap);
+                A.take(&g.pid, cap);
+                A.take(&g.tail, cap * RNG_TAIL);
+                A.take(&g.q_ovf, cap);
+                A.take(&g.ovf_counter, (size_t)4);
+            }
+        }
+        A.take(&P.hit_t, cap); A.take(&P.hit_u, cap); A.take(&P.hit_v, cap); A.take(&P.hit_id, cap);
+        if (mode == HNM_MODE_PATHTRACING) {
+            A.take(&P.q_miss, cap); A.take(&P.q_delta, cap); A.take(&P.q_nee, cap);
+            for (int k = 0; k < 3; k++) {
+                A.take(&P.ev_thr[k], cap); A.take(&P.ev_albedo[k], cap); A.take(&P.ev_emission[k], cap);
+                A.take(&P.s_pos[k], scap);
+            }
+            A.take(&P.ev_pid, cap);
+            for (int k = 0; k < 6; k++) A.take(&P.sray[k], scap);
+            A.take(&P.s_bsdf, scap); A.take(&P.s_g, scap); A.take(&P.s_tmax, scap);
+        }
+        A.take(&r->cand.id, nl * TRACE_CAND); A.take(&r->cand.lo, nl * TRACE_CAND);
+        A.take(&r->cand.n, nl); A.take(&r->cand.ub, nl);
+        A.take(&P.counters, (size_t)NUM_COUNTERS);
+        A.take(&P.stats, (size_t)S_COUNT);
+        A.take(&P.accum, accum_n);
+    };
+    {
+        Arena measure;
+        layout(measure);
+        char* base = nullptr;
+        if ((rc = dev_alloc(r->allocs, &base, measure.off))) return bail(rc);
+        Arena place;
+        place.base = base;
+        layout(place);
     }
     for (int s = 0; s < r->num_gen; s++) {
         hnm_renderer::GenSet& g = r->gen[s];
-        for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &g.L[k], cap))) return bail(rc);
-        if ((rc = dev_alloc(A, &g.cursor, cap))) return bail(rc);
-        if (mode == HNM_MODE_PATHTRACING) {
-            for (int k = 0; k < 6; k++) if ((rc = dev_alloc(A, &g.ray[k], cap))) return bail(rc);
-            for (int k = 0; k < 3; k++) if ((rc = dev_alloc(A, &g.thr[k], cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &g.pid, cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &g.tail, cap * RNG_TAIL))) return bail(rc);
-            if ((rc = dev_alloc(A, &g.q_ovf, cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &g.ovf_counter, (size_t)4))) return bail(rc);
-        }
         if (cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&g.released, cudaEventDisableTiming) != cudaSuccess) {
             set_error(HNM_ERR_CUDA, "cudaEventCreate failed");
@@ -442,40 +585,6 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     }
     if (cudaEventCreateWithFlags(&r->rng_gate, cudaEventDisableTiming) != cudaSuccess) { set_error(HNM_ERR_CUDA, "cudaEventCreate failed"); return bail(HNM_ERR_CUDA); }
     bind_gen_set(P, r->gen[0]);
-    if ((rc = dev_alloc(A, &P.hit_t, cap))) return bail(rc);
-    if ((rc = dev_alloc(A, &P.hit_u, cap))) return bail(rc);
-    if ((rc = dev_alloc(A, &P.hit_v, cap))) return bail(rc);
-    if ((rc = dev_alloc(A, &P.hit_id, cap))) return bail(rc);
-    if (mode == HNM_MODE_PATHTRACING) {
-        if ((rc = dev_alloc(A, &P.q_miss, cap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.q_delta, cap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.q_nee, cap))) return bail(rc);
-        size_t scap = cap * std::max<uint32_t>(scene->num_emissions, 1);
-        for (int k = 0; k < 3; k++) {
-            if ((rc = dev_alloc(A, &P.ev_thr[k], cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &P.ev_albedo[k], cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &P.ev_emission[k], cap))) return bail(rc);
-            if ((rc = dev_alloc(A, &P.s_pos[k], scap))) return bail(rc);
-        }
-        if ((rc = dev_alloc(A, &P.ev_pid, cap))) return bail(rc);
-        for (int k = 0; k < 6; k++) if ((rc = dev_alloc(A, &P.sray[k], scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.s_bsdf, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.s_g, scap))) return bail(rc);
-        if ((rc = dev_alloc(A, &P.s_tmax, scap))) return bail(rc);
-    }
-    {
-        size_t nl = cap + (mode == HNM_MODE_PATHTRACING ? cap * std::max<uint32_t>(scene->num_emissions, 1) : 0);
-        if (nl >= (1ull << 32)) { set_error(HNM_ERR_INVALID, "too many rays in flight for 32-bit list slots"); return bail(HNM_ERR_INVALID); }
-        r->cand.stride = (uint32_t)nl;
-        if ((rc = dev_alloc(A, &r->cand.id, nl * TRACE_CAND))) return bail(rc);
-        if ((rc = dev_alloc(A, &r->cand.lo, nl * TRACE_CAND))) return bail(rc);
-        if ((rc = dev_alloc(A, &r->cand.n, nl))) return bail(rc);
-        if ((rc = dev_alloc(A, &r->cand.ub, nl))) return bail(rc);
-    }
-    if ((rc = dev_alloc(A, &P.counters, (size_t)NUM_COUNTERS))) return bail(rc);
-    if ((rc = dev_alloc(A, &P.stats, (size_t)S_COUNT))) return bail(rc);
-    size_t accum_n = (size_t)r->padded_rows * width * 3;
-    if ((rc = dev_alloc(A, &P.accum, accum_n))) return bail(rc);
     ce = cudaMemsetAsync(P.accum, 0, accum_n * sizeof(double), r->stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(P.stats, 0, S_COUNT * sizeof(unsigned long long), r->stream);
     if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
@@ -561,17 +670,25 @@ int hnm_deinterleave(hnm_renderer* r, const void* gathered, void* full) {
     return 0;
 }
 
-int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t sampling, uint8_t* rgb8) {
-    if (!r || !rgb8) return set_error(HNM_ERR_INVALID, "null argument");
-    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
-    if (!accum_full_device && r->P.nranks != 1) return set_error(HNM_ERR_STATE, "a sharded renderer needs the gathered full-image buffer");
-    HNM_CUDA(cudaSetDevice(r->scene->device));
+// update_imgbuf on the renderer's stream: tone map + gamma, bilateral, quantise into r->rgb8 (device) and from
+// there into the renderer's pinned staging buffer.  Asynchronous; the caller synchronises the stream.
+static int enqueue_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t sampling) {
     size_t n = (size_t)r->P.W * r->P.H;
-    int rc = 0;
-    if (!r->tmp0) {
-        if ((rc = dev_alloc(r->allocs, &r->tmp0, n * 3))) return rc;
-        if ((rc = dev_alloc(r->allocs, &r->tmp1, n * 3))) return rc;
-        if ((rc = dev_alloc(r->allocs, &r->rgb8, n * 3))) return rc;
+    if (!r->tmp0 || !r->tmp1 || !r->rgb8 || !r->rgb8_host) {
+        // all or nothing: a partial failure must not leave a half-initialised set behind for the next call
+        double *t0 = nullptr, *t1 = nullptr;
+        uint8_t *d8 = nullptr, *h8 = nullptr;
+        cudaError_t e = cudaMalloc(&t0, n * 3 * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&t1, n * 3 * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&d8, n * 3);
+        if (e == cudaSuccess) e = cudaMallocHost(&h8, n * 3);
+        if (e != cudaSuccess) {
+            cudaFree(t0); cudaFree(t1); cudaFree(d8);
+            if (h8) cudaFreeHost(h8);
+            return set_error(HNM_ERR_NOMEM, std::string("resolve buffers: ") + cudaGetErrorString(e));
+        }
+        r->allocs.push_back(t0); r->allocs.push_back(t1); r->allocs.push_back(d8);
+        r->tmp0 = t0; r->tmp1 = t1; r->rgb8 = d8; r->rgb8_host = h8;
     }
     ResolveParams R;
     R.accum = accum_full_device ? (const double*)accum_full_device : r->P.accum;
@@ -590,8 +707,19 @@ int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t samplin
     }
     launch_timed(r, "quantise", [&] { k_quantise<<<grid, 256, 0, st>>>(R, src); });
     HNM_CUDA(cudaGetLastError());
-    HNM_CUDA(cudaMemcpyAsync(rgb8, r->rgb8, n * 3, cudaMemcpyDeviceToHost, st));
-    HNM_CUDA(cudaStreamSynchronize(st));
+    HNM_CUDA(cudaMemcpyAsync(r->rgb8_host, r->rgb8, n * 3, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
+int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t sampling, uint8_t* rgb8) {
+    if (!r || !rgb8) return set_error(HNM_ERR_INVALID, "null argument");
+    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
+    if (!accum_full_device && r->P.nranks != 1) return set_error(HNM_ERR_STATE, "a sharded renderer needs the gathered full-image buffer");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    int rc = enqueue_resolve(r, accum_full_device, sampling);
+    if (rc) return rc;
+    HNM_CUDA(cudaStreamSynchronize(r->stream));
+    memcpy(rgb8, r->rgb8_host, (size_t)r->P.W * r->P.H * 3);
     return 0;
 }
 
@@ -643,6 +771,179 @@ int hnm_get_kernel_times(hnm_renderer* r, uint32_t max, const char** names, floa
     return 0;
 }
 
+// ---- multi-GPU behind the boundary -------------------------------------------------------------------------
+// (a) one process, N devices: what a single-process host (the Rust binary) calls instead of hnm_renderer_*.
+int hnm_group_create(const hnm_scene_desc* desc, const hnm_camera* camera, uint32_t width, uint32_t height, int mode,
+                     uint32_t num_devices, const int* devices, uint32_t tile_rows, uint32_t max_batch, hnm_group** out) {
+    if (!desc || !camera || !out || !devices) return set_error(HNM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (num_devices == 0 || num_devices > 64) return set_error(HNM_ERR_INVALID, "bad device count");
+    if (tile_rows == 0) tile_rows = 4;
+    SceneBuilder b(desc);
+    int rc = scene_build_host(desc, b);  // validated and re-laid out ONCE, uploaded to every device
+    if (rc) return rc;
+    hnm_group* g = new hnm_group();
+    g->W = width; g->H = height;
+    auto bail = [&](int code) { hnm_group_destroy(g); return code; };
+    for (uint32_t k = 0; k < num_devices; k++) {
+        hnm_scene* sc = nullptr;
+        if ((rc = scene_upload(desc, b, devices[k], &sc))) return bail(rc);
+        g->scenes.push_back(sc);
+        hnm_shard sh = {k, num_devices, tile_rows, 0};
+        hnm_renderer* r = nullptr;
+        if ((rc = hnm_renderer_create(sc, camera, width, height, mode, &sh, max_batch, &r))) return bail(rc);
+        g->rs.push_back(r);
+        cudaEvent_t ev = nullptr;
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { set_error(HNM_ERR_CUDA, "cudaEventCreate failed"); return bail(HNM_ERR_CUDA); }
+        g->copied.push_back(ev);
+    }
+    // direct NVLink stores into device 0 for the gather (without peer access the copies are staged by the driver)
+    for (uint32_t k = 1; k < num_devices; k++) {
+        if (devices[k] == devices[0]) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, devices[k], devices[0]);
+        if (can) {
+            cudaSetDevice(devices[k]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+            if (e != cudaSuccess) cudaGetLastError();  // already enabled: fine
+        }
+    }
+    *out = g;
+    return 0;
+}
+void hnm_group_destroy(hnm_group* g) {
+    if (!g) return;
+    for (auto r : g->rs) hnm_renderer_destroy(r);
+    for (auto s : g->scenes) hnm_scene_destroy(s);
+    for (auto e : g->copied) if (e) cudaEventDestroy(e);
+    delete g;
+}
+uint32_t hnm_group_size(const hnm_group* g) { return g ? (uint32_t)g->rs.size() : 0; }
+hnm_renderer* hnm_group_member(hnm_group* g, uint32_t k) { return (g && k < g->rs.size()) ? g->rs[k] : nullptr; }
+int hnm_group_render_passes(hnm_group* g, uint32_t sampling_first, uint32_t count) {
+    if (!g) return set_error(HNM_ERR_INVALID, "null group");
+    for (auto r : g->rs) { int rc = hnm_render_passes(r, sampling_first, count); if (rc) return rc; }  // asynchronous on every device
+    return 0;
+}
+int hnm_group_synchronize(hnm_group* g) {
+    if (!g) return set_error(HNM_ERR_INVALID, "null group");
+    for (auto r : g->rs) { int rc = hnm_synchronize(r); if (rc) return rc; }
+    return 0;
+}
+int hnm_group_clear(hnm_group* g) {
+    if (!g) return set_error(HNM_ERR_INVALID, "null group");
+    for (auto r : g->rs) { int rc = hnm_clear(r); if (rc) return rc; }
+    return 0;
+}
+// shards -> device 0 (peer copies, each on its source device's stream, i.e. after that device's passes), then the
+// image in row order on device 0's stream.  Asynchronous.
+static int group_gather(hnm_group* g, const double** full) {
+    hnm_renderer* r0 = g->rs[0];
+    if (g->rs.size() == 1) { *full = r0->P.accum; return 0; }
+    HNM_CUDA(cudaSetDevice(r0->scene->device));
+    int rc = ensure_gather_buffers(r0);
+    if (rc) return rc;
+    const size_t shard = (size_t)r0->padded_rows * r0->P.W * 3;
+    for (size_t k = 0; k < g->rs.size(); k++) {
+        hnm_renderer* r = g->rs[k];
+        HNM_CUDA(cudaSetDevice(r->scene->device));
+        HNM_CUDA(cudaMemcpyPeerAsync(r0->gathered + k * shard, r0->scene->device, r->P.accum, r->scene->device, shard * sizeof(double), r->stream));
+        HNM_CUDA(cudaEventRecord(g->copied[k], r->stream));
+    }
+    HNM_CUDA(cudaSetDevice(r0->scene->device));
+    for (size_t k = 1; k < g->rs.size(); k++) HNM_CUDA(cudaStreamWaitEvent(r0->stream, g->copied[k], 0));
+    k_deinterleave<<<r0->sm_count * 4, 256, 0, r0->stream>>>(r0->gathered, r0->full, r0->P.W, r0->P.H, r0->padded_rows, r0->P.nranks, r0->P.tile_rows);
+    HNM_CUDA(cudaGetLastError());
+    *full = r0->full;
+    return 0;
+}
+int hnm_group_resolve(hnm_group* g, uint32_t sampling, uint8_t* rgb8) {
+    if (!g || !rgb8) return set_error(HNM_ERR_INVALID, "null argument");
+    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
+    const double* full = nullptr;
+    int rc = group_gather(g, &full);
+    if (rc) return rc;
+    hnm_renderer* r0 = g->rs[0];
+    if ((rc = enqueue_resolve(r0, full, sampling))) return rc;   // on device 0 only
+    HNM_CUDA(cudaStreamSynchronize(r0->stream));
+    memcpy(rgb8, r0->rgb8_host, (size_t)g->W * g->H * 3);
+    return 0;
+}
+int hnm_group_read_accum(hnm_group* g, double* rgb) {
+    if (!g || !rgb) return set_error(HNM_ERR_INVALID, "null argument");
+    const double* full = nullptr;
+    int rc = group_gather(g, &full);
+    if (rc) return rc;
+    hnm_renderer* r0 = g->rs[0];
+    HNM_CUDA(cudaMemcpyAsync(rgb, full, (size_t)g->W * g->H * 3 * sizeof(double), cudaMemcpyDeviceToHost, r0->stream));
+    HNM_CUDA(cudaStreamSynchronize(r0->stream));
+    return 0;
+}
+int hnm_group_get_counters(hnm_group* g, hnm_counters* out) {
+    if (!g || !out) return set_error(HNM_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    for (auto r : g->rs) {
+        hnm_counters c;
+        int rc = hnm_get_counters(r, &c);
+        if (rc) return rc;
+        out->paths += c.paths; out->segments += c.segments; out->shadow_rays += c.shadow_rays; out->rng_fallbacks += c.rng_fallbacks;
+        out->kernel_launches += c.kernel_launches; out->node_visits += c.node_visits; out->prim_tests += c.prim_tests;
+    }
+    return 0;
+}
+
+// (b) one process per device (torchrun / MPI style): the one exchange step of the path, an NCCL all-gather of the f64
+// accumulation shards, enqueued on the renderer's own stream right behind its passes.
+int hnm_dist_unique_id(uint8_t* id) {
+    if (!id) return set_error(HNM_ERR_INVALID, "null argument");
+    if (!nccl().ok) return set_error(HNM_ERR_STATE, "NCCL unavailable: " + nccl().why);
+    NcclApi::UniqueId u;
+    HNM_NCCL(nccl().GetUniqueId(&u));
+    memcpy(id, u.internal, HNM_DIST_ID_BYTES);
+    return 0;
+}
+int hnm_dist_init(hnm_renderer* r, const uint8_t* id, uint32_t rank, uint32_t num_ranks) {
+    if (!r || !id) return set_error(HNM_ERR_INVALID, "null argument");
+    if (rank != r->P.rank || num_ranks != r->P.nranks) return set_error(HNM_ERR_INVALID, "rank / num_ranks differ from the renderer's shard");
+    if (!nccl().ok) return set_error(HNM_ERR_STATE, "NCCL unavailable: " + nccl().why);
+    if (r->nccl_comm) return set_error(HNM_ERR_STATE, "hnm_dist_init called twice");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    NcclApi::UniqueId u;
+    memcpy(u.internal, id, HNM_DIST_ID_BYTES);
+    HNM_NCCL(nccl().CommInitRank(&r->nccl_comm, (int)num_ranks, u, (int)rank));
+    r->dist_rank = rank; r->dist_nranks = num_ranks;
+    return ensure_gather_buffers(r);
+}
+static int dist_gather(hnm_renderer* r) {
+    if (!r->nccl_comm) return set_error(HNM_ERR_STATE, "hnm_dist_init has not been called");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    const size_t shard = (size_t)r->padded_rows * r->P.W * 3;
+    HNM_NCCL(nccl().AllGather(r->P.accum, r->gathered, shard, NCCL_FLOAT64, r->nccl_comm, r->stream));
+    k_deinterleave<<<r->sm_count * 4, 256, 0, r->stream>>>(r->gathered, r->full, r->P.W, r->P.H, r->padded_rows, r->P.nranks, r->P.tile_rows);
+    HNM_CUDA(cudaGetLastError());
+    return 0;
+}
+// Collective: every rank calls it.  Ranks that pass rgb8 == NULL only take part in the gather (asynchronously);
+// a rank that passes a buffer also runs update_imgbuf on the gathered image and returns it.
+int hnm_dist_resolve(hnm_renderer* r, uint32_t sampling, uint8_t* rgb8) {
+    if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
+    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
+    int rc = dist_gather(r);
+    if (rc || !rgb8) return rc;
+    if ((rc = enqueue_resolve(r, r->full, sampling))) return rc;
+    HNM_CUDA(cudaStreamSynchronize(r->stream));
+    memcpy(rgb8, r->rgb8_host, (size_t)r->P.W * r->P.H * 3);
+    return 0;
+}
+int hnm_dist_read_accum(hnm_renderer* r, double* rgb) {
+    if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
+    int rc = dist_gather(r);
+    if (rc || !rgb) return rc;
+    HNM_CUDA(cudaMemcpyAsync(rgb, r->full, (size_t)r->P.W * r->P.H * 3 * sizeof(double), cudaMemcpyDeviceToHost, r->stream));
+    HNM_CUDA(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+
 // ---- batch entry points -----------------------------------------------------------------------
 int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_hit* hits) {
     if (!scene || !rays || !hits) return set_error(HNM_ERR_INVALID, "null argument");
@@ -681,11 +982,11 @@ int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_h
     A.stats = dstats;
     A.stat_segments = -1; A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
     A.cand = cl;
-    k_trace<false><<<148 * HNM_TRACE_MIN_BLOCKS, TRACE_THREADS>>>(scene->d, A);
-    k_confirm<false><<<148 * 8, 256>>>(scene->d, A);
+    k_trace<false><<<scene->sm_count * HNM_TRACE_MIN_BLOCKS, TRACE_THREADS>>>(scene->d, A);
+    k_confirm<false><<<scene->sm_count * 8, 256>>>(scene->d, A);
     RayPtrs rp;
     for (int k = 0; k < 6; k++) rp.p[k] = ray[k];
-    k_hits_to_abi<<<592, 256>>>(scene->d, rp, ht, hu, hv, hid, n, dh);
+    k_hits_to_abi<<<scene->sm_count * 4, 256>>>(scene->d, rp, ht, hu, hv, hid, n, dh);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy(hits, dh, (size_t)n * sizeof(hnm_hit), cudaMemcpyDeviceToHost);
     cleanup();
@@ -693,27 +994,25 @@ int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_h
     return 0;
 }
 
-#define HNM_TMP_UPLOAD(ptr, host, bytes) \
-    HNM_CUDA(cudaMalloc(&ptr, std::max<size_t>(bytes, 16))); \
-    HNM_CUDA(cudaMemcpy(ptr, host, bytes, cudaMemcpyHostToDevice));
-
 int hnm_isaac64_batch(int device, const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
     if (!seeds || !out) return set_error(HNM_ERR_INVALID, "null argument");
     if (n == 0 || count == 0) return 0;
     HNM_CUDA(cudaSetDevice(device));
+    int sms = 0, rc = 0;
+    if ((rc = device_sm_count(device, &sms))) return rc;
+    TmpDev T;
     uint64_t *ds = nullptr, *dout = nullptr;
-    HNM_TMP_UPLOAD(ds, seeds, (size_t)n * 4 * sizeof(uint64_t));
-    HNM_CUDA(cudaMalloc(&dout, (size_t)n * count * sizeof(uint64_t)));
+    if ((rc = T.upload(&ds, seeds, (size_t)n * 4 * sizeof(uint64_t)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * count * sizeof(uint64_t)))) return rc;
     if (count <= HNM_RNG_TAIL) {
         size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
         HNM_CUDA(cudaFuncSetAttribute(k_isaac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_isaac_batch<<<148, ISAAC_THREADS, smem>>>(ds, n, count, dout);
+        k_isaac_batch<<<sms, ISAAC_THREADS, smem>>>(ds, n, count, dout);
     } else {
-        k_isaac_full_batch<<<148, 64>>>(ds, n, count, dout);  // the exact slow path, with refill
+        k_isaac_full_batch<<<sms, 64>>>(ds, n, count, dout);  // the exact slow path, with refill
     }
     HNM_CUDA(cudaGetLastError());
     HNM_CUDA(cudaMemcpy(out, dout, (size_t)n * count * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    cudaFree(ds); cudaFree(dout);
     return 0;
 }
 static void default_math_scene(DScene& sc) {
@@ -724,42 +1023,82 @@ int hnm_material_sample_batch(int device, const double* in, uint32_t n, double* 
     if (!in || !out) return set_error(HNM_ERR_INVALID, "null argument");
     if (n == 0) return 0;
     HNM_CUDA(cudaSetDevice(device));
+    int sms = 0, rc = 0;
+    if ((rc = device_sm_count(device, &sms))) return rc;
+    TmpDev T;
     double *di = nullptr, *dout = nullptr;
-    HNM_TMP_UPLOAD(di, in, (size_t)n * 14 * sizeof(double));
-    HNM_CUDA(cudaMalloc(&dout, (size_t)n * 8 * sizeof(double)));
+    if ((rc = T.upload(&di, in, (size_t)n * 14 * sizeof(double)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * 8 * sizeof(double)))) return rc;
     DScene sc;
     default_math_scene(sc);
-    k_material_sample_batch<<<296, 256>>>(sc, di, n, dout);
+    k_material_sample_batch<<<sms * 2, 256>>>(sc, di, n, dout);
     HNM_CUDA(cudaGetLastError());
     HNM_CUDA(cudaMemcpy(out, dout, (size_t)n * 8 * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(di); cudaFree(dout);
     return 0;
 }
 int hnm_material_bsdf_batch(int device, const double* in, uint32_t n, double* out) {
     if (!in || !out) return set_error(HNM_ERR_INVALID, "null argument");
     if (n == 0) return 0;
     HNM_CUDA(cudaSetDevice(device));
+    int sms = 0, rc = 0;
+    if ((rc = device_sm_count(device, &sms))) return rc;
+    TmpDev T;
     double *di = nullptr, *dout = nullptr;
-    HNM_TMP_UPLOAD(di, in, (size_t)n * 12 * sizeof(double));
-    HNM_CUDA(cudaMalloc(&dout, (size_t)n * sizeof(double)));
-    k_material_bsdf_batch<<<296, 256>>>(di, n, dout);
+    if ((rc = T.upload(&di, in, (size_t)n * 12 * sizeof(double)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * sizeof(double)))) return rc;
+    k_material_bsdf_batch<<<sms * 2, 256>>>(di, n, dout);
     HNM_CUDA(cudaGetLastError());
     HNM_CUDA(cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(di); cudaFree(dout);
     return 0;
 }
 int hnm_math_batch(int device, int fn, const double* x, const double* y, uint32_t n, double* out) {
     if (!x || !y || !out) return set_error(HNM_ERR_INVALID, "null argument");
     if (n == 0) return 0;
     HNM_CUDA(cudaSetDevice(device));
+    int sms = 0, rc = 0;
+    if ((rc = device_sm_count(device, &sms))) return rc;
+    TmpDev T;
     double *dx = nullptr, *dy = nullptr, *dout = nullptr;
-    HNM_TMP_UPLOAD(dx, x, (size_t)n * sizeof(double));
-    HNM_TMP_UPLOAD(dy, y, (size_t)n * sizeof(double));
-    HNM_CUDA(cudaMalloc(&dout, (size_t)n * sizeof(double)));
-    k_math_batch<<<296, 256>>>(fn, dx, dy, n, dout);
+    if ((rc = T.upload(&dx, x, (size_t)n * sizeof(double)))) return rc;
+    if ((rc = T.upload(&dy, y, (size_t)n * sizeof(double)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * sizeof(double)))) return rc;
+    k_math_batch<<<sms * 2, 256>>>(fn, dx, dy, n, dout);
     HNM_CUDA(cudaGetLastError());
     HNM_CUDA(cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return 0;
+}
+// `Texture::sample` (src/texture.rs:108-114: bilinear on the gamma-space texels, v flip, u32 wrap at the top row,
+// pow 2.2, times the tint) on n independent (u, v) pairs; image < 0 = a constant-colour texture
+int hnm_texture_sample_batch(hnm_scene* scene, int32_t image, const double* tint, const double* uv, uint32_t n, double* rgb) {
+    if (!scene || !tint || !uv || !rgb) return set_error(HNM_ERR_INVALID, "null argument");
+    if (image >= (int32_t)scene->num_images) return set_error(HNM_ERR_INVALID, "bad image index");
+    if (n == 0) return 0;
+    HNM_CUDA(cudaSetDevice(scene->device));
+    TmpDev T;
+    int rc = 0;
+    double *duv = nullptr, *dout = nullptr;
+    if ((rc = T.upload(&duv, uv, (size_t)n * 2 * sizeof(double)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * 3 * sizeof(double)))) return rc;
+    DTexture t;
+    t.r = tint[0]; t.g = tint[1]; t.b = tint[2]; t.image = image < 0 ? -1 : image; t._pad = 0;
+    k_texture_sample_batch<<<scene->sm_count * 2, 256>>>(scene->d, t, duv, n, dout);
+    HNM_CUDA(cudaGetLastError());
+    HNM_CUDA(cudaMemcpy(rgb, dout, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+// `Skybox::sample` (src/scene.rs:295-319) on n directions (xyz triples, not normalised by the callee)
+int hnm_skybox_sample_batch(hnm_scene* scene, const double* directions, uint32_t n, double* rgb) {
+    if (!scene || !directions || !rgb) return set_error(HNM_ERR_INVALID, "null argument");
+    if (n == 0) return 0;
+    HNM_CUDA(cudaSetDevice(scene->device));
+    TmpDev T;
+    int rc = 0;
+    double *dd = nullptr, *dout = nullptr;
+    if ((rc = T.upload(&dd, directions, (size_t)n * 3 * sizeof(double)))) return rc;
+    if ((rc = T.alloc(&dout, (size_t)n * 3 * sizeof(double)))) return rc;
+    k_skybox_sample_batch<<<scene->sm_count * 2, 256>>>(scene->d, dd, n, dout);
+    HNM_CUDA(cudaGetLastError());
+    HNM_CUDA(cudaMemcpy(rgb, dout, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

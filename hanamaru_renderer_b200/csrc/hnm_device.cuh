@@ -118,6 +118,16 @@ HNM_D DTri load_tri(const DTri* p) {
     return t;
 }
 
+// One node of the HOST's (reference-topology) trees, top level first, then every mesh: f64 box as the reference built
+// it + link to the parent.  The reference tests a primitive only if every box from the root down to its leaf passes
+// Aabb::intersect_ray (src/bvh.rs:214,240); see chain_pass below.
+struct RefNode {
+    double box[6];    // min xyz, max xyz
+    uint32_t parent;  // REF_NONE at the top-level root; a mesh root's parent is the top-level leaf that lists its element
+    uint32_t _pad;
+};
+constexpr uint32_t REF_NONE = 0xFFFFFFFFu;
+
 struct DScene {
     const DNode* nodes;
     const DTri* tris;
@@ -141,6 +151,13 @@ struct DScene {
     uint32_t bounce_limit, supersampling;
     float far_limit;  // |origin| beyond this: advance the ray to the scene box before the f32 traversal
     double bounds_lo[3], bounds_hi[3];
+    // the reference's box chain (chain_pass)
+    const double* tri_box;      // [6] per triangle (reference leaf order): the box of the mesh leaf that lists it
+    const uint32_t* tri_leaf;   // that leaf's index in ref_nodes
+    const double* elem_box;     // [6] per element: the box of the top-level leaf that lists it
+    const uint32_t* elem_leaf;
+    const RefNode* ref_nodes;
+    uint32_t chain_full;        // the caller's boxes are not nested (child inside parent): always walk the whole chain
 };
 
 // closest hit, before material resolution
@@ -150,11 +167,62 @@ struct Hit {
     uint32_t id;    // triangle index (leaf order) or element id
 };
 
+// ---------------------------------------------------------------- the reference's box chain
+// src/bvh.rs:20-39 on a stored box with the ray's reciprocal direction; also returns tmax
+HNM_D bool ref_box_hit(const double* __restrict__ b, D3 o, double ix, double iy, double iz, double& tmax) {
+    const double t1 = (__ldg(b + 0) - o.x) * ix, t2 = (__ldg(b + 3) - o.x) * ix;
+    const double t3 = (__ldg(b + 1) - o.y) * iy, t4 = (__ldg(b + 4) - o.y) * iy;
+    const double t5 = (__ldg(b + 2) - o.z) * iz, t6 = (__ldg(b + 5) - o.z) * iz;
+    const double tmin = fmax(fmax(fmin(t1, t2), fmin(t3, t4)), fmin(t5, t6));  // f64::min / max ignore a NaN operand, like fmin / fmax
+    tmax = fmin(fmin(fmax(t1, t2), fmax(t3, t4)), fmax(t5, t6));
+    return tmin <= tmax && !(__double2hiint(tmax) < 0);
+}
+HNM_D bool ref_chain_full(const RefNode* __restrict__ nodes, uint32_t node, D3 o, double ix, double iy, double iz) {
+    while (node != REF_NONE) {
+        double tmax;
+        if (!ref_box_hit(nodes[node].box, o, ix, iy, iz, tmax)) return false;
+        node = nodes[node].parent;
+    }
+    return true;
+}
+// Would the reference have reached this primitive?  It tests a primitive only after EVERY box from the root of the top-level
+// tree down to the primitive's leaf passed Aabb::intersect_ray for this ray (src/bvh.rs:214,240), and that test is
+// not the geometric one: 0 * inf = NaN when a direction component is zero and the origin lies on a box plane, and the
+// roundings of a grazing ray can make tmin > tmax for a box the ray does touch.  The GPU traversal (another tree,
+// conservative f32 boxes) only proposes candidates, so the chain is re-checked here for every primitive whose exact test
+// passed.  `box6` = the primitive's LEAF box: boxes are nested (the builder merges children, src/bvh.rs:79-105) and
+// fl((plane - o) * inv) is monotone in `plane`, so with finite reciprocals tmin(ancestor) <= tmin(leaf) and
+// tmax(ancestor) >= tmax(leaf): the leaf passing implies every ancestor passing -- except for the sign of a zero tmax,
+// and except when a reciprocal is infinite (NaN terms are dropped by min / max): those walk the whole chain.
+// (Out of line: it runs once per ACCEPTED candidate, about once per ray; inlined into the candidate loops it cost the
+// confirming kernels registers they do not have.)
+__device__ __noinline__ bool chain_pass_impl(const RefNode* __restrict__ nodes, uint32_t chain_full, const double* __restrict__ box6,
+                                             const uint32_t* __restrict__ leaf, double ox, double oy, double oz, double dx, double dy, double dz) {
+    const D3 o = D3{ox, oy, oz};
+    const double ix = 1.0 / dx, iy = 1.0 / dy, iz = 1.0 / dz;
+    const bool finite = fabs(ix) <= 1.79769313486231570815e308 && fabs(iy) <= 1.79769313486231570815e308 && fabs(iz) <= 1.79769313486231570815e308;
+    if (finite && !chain_full) {
+        double tmax;
+        if (!ref_box_hit(box6, o, ix, iy, iz, tmax)) return false;
+        if (tmax != 0.0) return true;
+    }
+    return ref_chain_full(nodes, __ldg(leaf), o, ix, iy, iz);
+}
+HNM_D bool chain_pass(const DScene& sc, const double* __restrict__ box6, const uint32_t* __restrict__ leaf, D3 o, D3 dir) {
+    return chain_pass_impl(sc.ref_nodes, sc.chain_full, box6, leaf, o.x, o.y, o.z, dir.x, dir.y, dir.z);
+}
+// a ray for which the f32 candidate search must not cull by "certain" hits: its chain tests may produce NaN terms
+HNM_D bool ray_needs_exact_path(const DScene& sc, D3 dir) {
+    const double ix = 1.0 / dir.x, iy = 1.0 / dir.y, iz = 1.0 / dir.z;
+    const bool finite = fabs(ix) <= 1.79769313486231570815e308 && fabs(iy) <= 1.79769313486231570815e308 && fabs(iz) <= 1.79769313486231570815e308;
+    return !finite || sc.chain_full != 0u;
+}
+
 // ---------------------------------------------------------------- primitive tests (f64, reference arithmetic)
 // src/bvh.rs:266-290 with the running `intersection.distance` = best.t.  The reference keeps the LAST
 // candidate in DFS order among exact ties (`t > distance` rejects); with any visiting order that is
 // "larger leaf-order index wins" (SURVEY 7.2 hard part 3).
-HNM_D void tri_test(const DTri& tr, uint32_t g, D3 o, D3 dir, Hit& best) {
+HNM_D void tri_test(const DScene& sc, const DTri& tr, uint32_t g, D3 o, D3 dir, Hit& best) {
     D3 ray_inv = -dir;
     D3 edge1 = d3(tr.e1x, tr.e1y, tr.e1z);
     D3 edge2 = d3(tr.e2x, tr.e2y, tr.e2z);
@@ -169,11 +237,12 @@ HNM_D void tri_test(const DTri& tr, uint32_t g, D3 o, D3 dir, Hit& best) {
     double t = det(edge1, edge2, d) * denominator_inv;
     if (t < 0.0 || t > best.t) return;
     if (t == best.t && best.kind == LEAF_TRI && g < best.id) return;  // an earlier triangle loses an exact tie
+    if (!chain_pass(sc, sc.tri_box + 6 * (size_t)g, sc.tri_leaf + g, o, dir)) return;  // the reference never got to this triangle
     best.t = t; best.u = u; best.v = v; best.kind = LEAF_TRI; best.id = g;
 }
 
 // src/scene.rs:58-78 (acceptance only; normal/uv are recomputed for the winner)
-HNM_D void sphere_test(const DElement& e, uint32_t elem, const DElement* elements, D3 o, D3 dir, Hit& best) {
+HNM_D void sphere_test(const DScene& sc, const DElement& e, uint32_t elem, const DElement* elements, D3 o, D3 dir, Hit& best) {
     D3 a = o - d3(e.ax, e.ay, e.az);
     double b = dot(a, dir);
     double c = dot(a, a) - e.radius * e.radius;
@@ -183,7 +252,9 @@ HNM_D void sphere_test(const DElement& e, uint32_t elem, const DElement* element
         bool take = t < best.t;
         // exact tie with a later non-triangle element: the reference would have kept this (earlier) one
         if (!take && t == best.t && best.kind != LEAF_TRI && best.kind != LEAF_NONE && e.seq < elements[best.id].seq) take = true;
-        if (take) { best.t = t; best.u = 0.0; best.v = 0.0; best.kind = LEAF_SPHERE; best.id = elem; }
+        if (take && chain_pass(sc, sc.elem_box + 6 * (size_t)elem, sc.elem_leaf + elem, o, dir)) {
+            best.t = t; best.u = 0.0; best.v = 0.0; best.kind = LEAF_SPHERE; best.id = elem;
+        }
     }
 }
 
@@ -202,13 +273,15 @@ HNM_D bool aabb_intersect_ray(double mnx, double mny, double mnz, double mxx, do
     *distance = !signbit_(tmin) ? tmin : tmax;
     return hit;
 }
-HNM_D void cuboid_test(const DElement& e, uint32_t elem, const DElement* elements, D3 o, D3 dir, Hit& best) {
+HNM_D void cuboid_test(const DScene& sc, const DElement& e, uint32_t elem, const DElement* elements, D3 o, D3 dir, Hit& best) {
     double distance;
     bool hit = aabb_intersect_ray(e.ax, e.ay, e.az, e.bx, e.by, e.bz, o, dir, &distance);
     if (hit) {
         bool take = distance < best.t;
         if (!take && distance == best.t && best.kind != LEAF_TRI && best.kind != LEAF_NONE && e.seq < elements[best.id].seq) take = true;
-        if (take) { best.t = distance; best.u = 0.0; best.v = 0.0; best.kind = LEAF_CUBOID; best.id = elem; }
+        if (take && chain_pass(sc, sc.elem_box + 6 * (size_t)elem, sc.elem_leaf + elem, o, dir)) {
+            best.t = distance; best.u = 0.0; best.v = 0.0; best.kind = LEAF_CUBOID; best.id = elem;
+        }
     }
 }
 
@@ -288,14 +361,14 @@ HNM_D Hit trace(const DScene& sc, D3 o, D3 dir, TraceStats* st) {
                     uint32_t g = __ldg(sc.tri_perm + first + k);
                     DTri tr = load_tri(sc.tris + g);
                     if (STATS) st->prims++;
-                    tri_test(tr, g, o, dir, best);
+                    tri_test(sc, tr, g, o, dir, best);
                 }
             } else if (kind == LEAF_SPHERE) {
                 if (STATS) st->prims++;
-                sphere_test(sc.elements[first], first, sc.elements, o, dir, best);
+                sphere_test(sc, sc.elements[first], first, sc.elements, o, dir, best);
             } else if (kind == LEAF_CUBOID) {
                 if (STATS) st->prims++;
-                cuboid_test(sc.elements[first], first, sc.elements, o, dir, best);
+                cuboid_test(sc, sc.elements[first], first, sc.elements, o, dir, best);
             }
         }
         if (sp == 0) break;

@@ -835,6 +835,18 @@ __global__ void k_material_bsdf_batch(const double* in, uint32_t n, double* out)
         out[i] = bsdf(m, d3(p[3], p[4], p[5]), d3(p[6], p[7], p[8]), d3(p[9], p[10], p[11]));
     }
 }
+__global__ void k_texture_sample_batch(DScene sc, DTexture t, const double* uv, uint32_t n, double* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 c = texture_sample(sc, t, uv[2 * (size_t)i], uv[2 * (size_t)i + 1]);
+        out[3 * (size_t)i] = c.x; out[3 * (size_t)i + 1] = c.y; out[3 * (size_t)i + 2] = c.z;
+    }
+}
+__global__ void k_skybox_sample_batch(DScene sc, const double* dirs, uint32_t n, double* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        D3 c = skybox_sample(sc, d3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]));
+        out[3 * (size_t)i] = c.x; out[3 * (size_t)i + 1] = c.y; out[3 * (size_t)i + 2] = c.z;
+    }
+}
 __global__ void k_math_batch(int fn, const double* x, const double* y, uint32_t n, double* out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         double r;

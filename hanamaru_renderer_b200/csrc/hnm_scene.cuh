@@ -4,11 +4,13 @@
 #ifndef HNM_SCENE_CUH
 #define HNM_SCENE_CUH
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "hnm_device.cuh"
@@ -31,12 +33,14 @@ inline int set_error(int code, const std::string& msg) {
 
 struct hnm_scene {
     int device = 0;
+    int sm_count = 148;
     hnm::DScene d;
     hnm_config config;
     std::vector<void*> allocs;
     std::vector<cudaArray_t> arrays;
     std::vector<cudaTextureObject_t> texs;
-    uint32_t num_nodes = 0, num_tris = 0, num_elements = 0, num_emissions = 0;
+    uint32_t num_nodes = 0, num_tris = 0, num_elements = 0, num_emissions = 0, num_images = 0;
+    uint32_t tree_depth = 0;
     std::vector<int32_t> elem_surface;  // host copy, per element
 };
 
@@ -75,6 +79,11 @@ class SceneBuilder {
     std::vector<DTri> tris;
     std::vector<uint32_t> tri_elem, tri_face;
     std::vector<uint32_t> elem_seq;
+    // the reference's box chain (hnm_device.cuh: chain_pass)
+    std::vector<RefNode> ref_nodes;
+    std::vector<uint32_t> tri_leaf, elem_leaf;
+    std::vector<double> tri_box, elem_box;
+    bool chain_full = false;
     BoxD bounds;
     double pad = 0.0;
     std::string error;
@@ -87,7 +96,10 @@ class SceneBuilder {
         if (d->num_elements == 0 || !d->elements) return fail("scene has no elements");
         if (d->num_top_nodes == 0 || !d->top_nodes) return fail("scene has no top-level BVH");
         if (d->config.supersampling == 0 || d->config.supersampling > 8) return fail("supersampling out of range");
-        if (d->config.bounce_limit < 2 || d->config.bounce_limit > 64) return fail("bounce_limit out of range");
+        // every path consumes one pair of the random stream per lens iteration and per bounce (src/camera.rs:68,
+        // src/renderer.rs:175); HNM_RNG_TAIL words per path are stored, so 2 * (bounce_limit - 1) must fit
+        if (d->config.bounce_limit < 2 || 2 * (d->config.bounce_limit - 1) > HNM_RNG_TAIL)
+            return fail("bounce_limit out of range (2 .. 17: 2 * (bounce_limit - 1) words of the per-path random stream must fit HNM_RNG_TAIL)");
         for (uint32_t i = 0; i < d->num_elements; i++) {
             const hnm_element& e = d->elements[i];
             if (e.kind < 0 || e.kind > 2) return fail("bad element kind");
@@ -152,6 +164,26 @@ class SceneBuilder {
             if (elem_seq[order[s]] != 0xFFFFFFFFu) { error = "element listed twice in the top-level BVH"; return false; }
             elem_seq[order[s]] = s;
         }
+        // the host's trees as parent-linked nodes: top level first, then each mesh below the top-level leaf of its element
+        ref_nodes.clear();
+        ref_nodes.resize(d->num_top_nodes);
+        elem_leaf.assign(d->num_elements, REF_NONE);
+        auto set_ref = [&](uint32_t at, const hnm_bvh_node& n, uint32_t parent) {
+            for (int k = 0; k < 3; k++) { ref_nodes[at].box[k] = n.aabb_min[k]; ref_nodes[at].box[3 + k] = n.aabb_max[k]; }
+            ref_nodes[at].parent = parent;
+            ref_nodes[at]._pad = 0;
+        };
+        for (uint32_t n = 0; n < d->num_top_nodes; n++) set_ref(n, d->top_nodes[n], REF_NONE);
+        for (uint32_t n = 0; n < d->num_top_nodes; n++) {
+            const hnm_bvh_node& nd = d->top_nodes[n];
+            if (nd.child0 >= 0) { ref_nodes[nd.child0].parent = n; ref_nodes[nd.child1].parent = n; }
+            else for (uint32_t k = 0; k < nd.count; k++) elem_leaf[d->top_indices[nd.first + k]] = n;
+        }
+        elem_box.assign((size_t)d->num_elements * 6, 0.0);
+        for (uint32_t el = 0; el < d->num_elements; el++) {
+            if (elem_leaf[el] == REF_NONE) continue;  // not listed: unreachable for the reference too (never a candidate)
+            for (int k = 0; k < 6; k++) elem_box[(size_t)el * 6 + k] = ref_nodes[elem_leaf[el]].box[k];
+        }
         mesh_tri_base_.assign(d->num_meshes, 0);
         std::vector<char> mesh_used(d->num_meshes, 0);
         for (uint32_t el : order) {
@@ -163,6 +195,23 @@ class SceneBuilder {
             mesh_used[e.mesh] = 1;
             const hnm_mesh& m = d->meshes[e.mesh];
             mesh_tri_base_[e.mesh] = (uint32_t)tris.size();
+            {
+                const uint32_t nbase = (uint32_t)ref_nodes.size(), tbase = (uint32_t)tris.size();
+                ref_nodes.resize(nbase + m.node_count);
+                tri_leaf.resize(tbase + m.index_count, REF_NONE);
+                tri_box.resize((size_t)(tbase + m.index_count) * 6, 0.0);
+                for (uint32_t n = 0; n < m.node_count; n++) set_ref(nbase + n, d->mesh_nodes[m.node_offset + n], n == 0 ? elem_leaf[el] : REF_NONE);
+                for (uint32_t n = 0; n < m.node_count; n++) {
+                    const hnm_bvh_node& nd = d->mesh_nodes[m.node_offset + n];
+                    if (nd.child0 >= 0) { ref_nodes[nbase + nd.child0].parent = nbase + n; ref_nodes[nbase + nd.child1].parent = nbase + n; }
+                    else for (uint32_t k = 0; k < nd.count; k++) {
+                        tri_leaf[tbase + nd.first + k] = nbase + n;
+                        for (int c = 0; c < 6; c++) tri_box[(size_t)(tbase + nd.first + k) * 6 + c] = ref_nodes[nbase + n].box[c];
+                    }
+                }
+                for (uint32_t k = 0; k < m.index_count; k++)
+                    if (tri_leaf[tbase + k] == REF_NONE) { error = "mesh index entry not owned by any leaf"; return false; }
+            }
             const double* vb = d->vertices + 3 * (size_t)m.vertex_offset;
             for (uint32_t k = 0; k < m.index_count; k++) {
                 uint32_t face = d->mesh_indices[m.index_offset + k];
@@ -204,8 +253,37 @@ class SceneBuilder {
             set_child(n, 1, leaf_link(LEAF_NONE, 0, 0), none);
             nodes[0] = n;
         }
+        // the traversal kernels keep the far child of every level on a stack of HNM_STACK entries: a deeper tree
+        // (a degenerate caller-supplied topology under HNM_BVH=ref, or pathological geometry) is refused, not truncated
+        depth = 0;
+        {
+            std::vector<std::pair<int32_t, uint32_t>> st;
+            st.push_back({0, 1u});
+            while (!st.empty()) {
+                auto [idx, dep] = st.back();
+                st.pop_back();
+                depth = std::max(depth, dep);
+                const DNode& n = nodes[idx];
+                if (n.c0 >= 0) st.push_back({n.c0, dep + 1});
+                if (n.c1 >= 0) st.push_back({n.c1, dep + 1});
+            }
+        }
+        if (depth > HNM_STACK) { error = "BVH deeper than the traversal stack (" + std::to_string(depth) + " > " + std::to_string(HNM_STACK) + " levels)"; return false; }
+        // chain_pass relies on nested boxes (child inside parent, as the reference's builder produces them by merging);
+        // a description whose boxes are not nested still renders exactly, on the slow path that walks every chain
+        chain_full = false;
+        for (const RefNode& n : ref_nodes) {
+            if (n.parent == REF_NONE) continue;
+            const RefNode& p = ref_nodes[n.parent];
+            const bool empty = !(n.box[0] <= n.box[3] && n.box[1] <= n.box[4] && n.box[2] <= n.box[5]);
+            if (empty) continue;
+            for (int k = 0; k < 3; k++)
+                if (!(n.box[k] >= p.box[k] && n.box[3 + k] <= p.box[3 + k])) chain_full = true;
+        }
+        if (getenv("HNM_CHAIN_FULL")) chain_full = atoi(getenv("HNM_CHAIN_FULL")) != 0;  // A/B and tests
         return true;
     }
+    uint32_t depth = 0;
 
     std::vector<uint32_t> tri_order;  // traversal (leaf) position -> triangle index in the reference's leaf order
 
@@ -327,6 +405,7 @@ class SceneBuilder {
         for (uint32_t el = 0; el < d_->num_elements; el++) {
             const hnm_element& e = d_->elements[el];
             if (e.kind == HNM_ELEM_MESH) continue;
+            if (elem_seq[el] == 0xFFFFFFFFu) continue;  // not listed in the top-level tree: the reference never tests it
             Prim p;
             p.box = element_box(e);
             if (p.box.empty) continue;
@@ -453,15 +532,30 @@ inline void scene_free(hnm_scene* s) {
     delete s;
 }
 
+// host part of hnm_scene_create: validation + re-layout (no CUDA call); one build serves every device of a group
+inline int scene_build_host(const hnm_scene_desc* desc, SceneBuilder& b) {
+    if (!b.validate()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    if (!b.build()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    (void)desc;
+    return 0;
+}
+inline int scene_upload(const hnm_scene_desc* desc, const SceneBuilder& b, int device, hnm_scene** out);
 inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out) {
     if (!out) return set_error(HNM_ERR_INVALID, "null output pointer");
     *out = nullptr;
     SceneBuilder b(desc);
-    if (!b.validate()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
-    if (!b.build()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    int rc = scene_build_host(desc, b);
+    if (rc) return rc;
+    return scene_upload(desc, b, device, out);
+}
+inline int scene_upload(const hnm_scene_desc* desc, const SceneBuilder& b, int device, hnm_scene** out) {
+    *out = nullptr;
     HNM_CUDA(cudaSetDevice(device));
+    int sm_count = 0;
+    HNM_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     hnm_scene* s = new hnm_scene();
     s->device = device;
+    s->sm_count = sm_count;
     s->config = desc->config;
     memset(&s->d, 0, sizeof(s->d));
     int rc = 0;
@@ -483,6 +577,12 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
         if ((rc = upload(s, tf, &s->d.trif))) return bail(rc);
         if ((rc = upload(s, b.tri_order, &s->d.tri_perm))) return bail(rc);
     }
+    if ((rc = upload(s, b.ref_nodes, &s->d.ref_nodes))) return bail(rc);
+    if ((rc = upload(s, b.tri_leaf, &s->d.tri_leaf))) return bail(rc);
+    if ((rc = upload(s, b.tri_box, &s->d.tri_box))) return bail(rc);
+    if ((rc = upload(s, b.elem_leaf, &s->d.elem_leaf))) return bail(rc);
+    if ((rc = upload(s, b.elem_box, &s->d.elem_box))) return bail(rc);
+    s->d.chain_full = b.chain_full ? 1u : 0u;
     if ((rc = upload(s, b.tri_elem, &s->d.tri_elem))) return bail(rc);
     if ((rc = upload(s, b.tri_face, &s->d.tri_face))) return bail(rc);
     std::vector<DElement> els(desc->num_elements);
@@ -581,7 +681,8 @@ inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out)
     s->d.far_limit = (float)(4.0 * R);
     s->d.scene_r = f32_up(R);
     s->num_nodes = (uint32_t)b.nodes.size(); s->num_tris = (uint32_t)b.tris.size();
-    s->num_elements = desc->num_elements; s->num_emissions = desc->num_emissions;
+    s->num_elements = desc->num_elements; s->num_emissions = desc->num_emissions; s->num_images = desc->num_images;
+    s->tree_depth = b.depth;
     *out = s;
     return 0;
 }

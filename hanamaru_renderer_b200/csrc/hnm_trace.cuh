@@ -269,7 +269,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
                         cur = 0;
                         lk = 0;
                         float fmaxo = fmaxf(fmaxf(fabsf((float)o.x), fabsf((float)o.y)), fabsf((float)o.z));
-                        if (fmaxo > sc.far_limit) {
+                        if (ray_needs_exact_path(sc, dir)) {
+                            // a zero (or subnormal) direction component: the reference's box tests contain 0 * inf = NaN terms
+                            // for this ray, so a hit that is "certain" geometrically may still be one the reference never
+                            // reaches.  No f32 culling: k_confirm / k_nee_resolve trace it exactly, chain checks included.
+                            HNM_FINISH(CAND_OVERFLOW)
+                        } else if (fmaxo > sc.far_limit) {
                             // the f32 origin would lose too many bits: advance it to the scene box first
                             double dist;
                             bool h = aabb_intersect_ray(sc.bounds_lo[0], sc.bounds_lo[1], sc.bounds_lo[2], sc.bounds_hi[0], sc.bounds_hi[1],
@@ -449,11 +454,11 @@ HNM_D Hit confirm_ray(const DScene& sc, const CandLists& cand, uint32_t slot, ui
             if (STATS) n_prims++;
             if (kind == LEAF_TRI) {
                 DTri tr = load_tri(sc.tris + id);
-                tri_test(tr, id, o, dir, best);
+                tri_test(sc, tr, id, o, dir, best);
             } else if (kind == LEAF_SPHERE) {
-                sphere_test(sc.elements[id], id, sc.elements, o, dir, best);
+                sphere_test(sc, sc.elements[id], id, sc.elements, o, dir, best);
             } else {
-                cuboid_test(sc.elements[id], id, sc.elements, o, dir, best);
+                cuboid_test(sc, sc.elements[id], id, sc.elements, o, dir, best);
             }
         }
     }

@@ -137,7 +137,7 @@ typedef struct hnm_config {
     double bilateral_sigma_i; /* 1.0 */
     double bilateral_sigma_s; /* 16.0 */
     uint32_t supersampling;        /* 2 */
-    uint32_t bounce_limit;         /* 10 -> `for _ in 1..10`, 9 segments */
+    uint32_t bounce_limit;         /* 10 -> `for _ in 1..10`, 9 segments; accepted range 2 .. 17 */
     uint32_t tone_mapping_mode;    /* 0 None, 1 Reinhard */
     uint32_t bilateral_iteration;  /* 1 */
     uint32_t bilateral_diameter;   /* 3 */
@@ -201,6 +201,7 @@ typedef struct hnm_counters {
 
 typedef struct hnm_scene hnm_scene;       /* opaque: device copy of a scene */
 typedef struct hnm_renderer hnm_renderer; /* opaque: wavefront state + accumulation buffer */
+typedef struct hnm_group hnm_group;       /* opaque: one scene copy + one renderer per device of ONE process */
 
 const char* hnm_last_error(void);
 uint32_t hnm_abi_version(void);
@@ -267,6 +268,55 @@ int hnm_set_profiling(hnm_renderer* r, int enabled);
 int hnm_mark(hnm_renderer* r, uint32_t slot);
 int hnm_elapsed_ms(hnm_renderer* r, uint32_t slot_a, uint32_t slot_b, float* ms);
 
+/* ---- multi-GPU ---------------------------------------
+ * `Renderer::render` is ONE call in ONE process (src/renderer.rs:25, called
+ * from src/main.rs:1216).  Every (pixel, sub-pixel, pass) is independent, so
+ * the image is sharded by interleaved row tiles (hnm_shard) with no data-path
+ * collective; the only exchange is the gather of the f64 accumulation shards
+ * before `update_imgbuf` (the 3x3 bilateral filter reads neighbouring rows).
+ * Each pixel has exactly one owner and passes are added in order, so the
+ * gathered buffer is bit-identical to a single-GPU render.
+ *
+ * (a) hnm_group_*: one process, one host thread, N devices -- what a
+ *     single-process host calls INSTEAD of hnm_scene_create / hnm_renderer_*.
+ *     The description is validated and re-laid out once and uploaded to every
+ *     device; passes are enqueued asynchronously on all devices; the shards
+ *     travel to device 0 as peer copies over NVLink and update_imgbuf runs on
+ *     device 0 only.  `devices` may name the same device more than once
+ *     (testing on a single GPU).  tile_rows 0 = default (4). */
+int hnm_group_create(const hnm_scene_desc* desc, const hnm_camera* camera,
+                     uint32_t width, uint32_t height, int mode,
+                     uint32_t num_devices, const int* devices,
+                     uint32_t tile_rows, uint32_t max_batch, hnm_group** out);
+void hnm_group_destroy(hnm_group* g);
+uint32_t hnm_group_size(const hnm_group* g);
+/* member k's renderer (counters, timing marks, profiling); owned by the group */
+hnm_renderer* hnm_group_member(hnm_group* g, uint32_t k);
+int hnm_group_render_passes(hnm_group* g, uint32_t sampling_first, uint32_t count);
+int hnm_group_synchronize(hnm_group* g);
+int hnm_group_clear(hnm_group* g);
+/* gather + `update_imgbuf` -> host rgb8 (width*height*3) */
+int hnm_group_resolve(hnm_group* g, uint32_t sampling, uint8_t* rgb8);
+/* gather -> the full accumulation buffer in image row order (width*height*3 f64, host) */
+int hnm_group_read_accum(hnm_group* g, double* rgb);
+int hnm_group_get_counters(hnm_group* g, hnm_counters* out); /* summed over the members */
+
+/* (b) hnm_dist_*: one process per device (torchrun / MPI launchers).  The
+ *     exchange step is ONE ncclAllGather of the accumulation shards on the
+ *     renderer's own stream (libnccl.so.2 is bound at run time; without it
+ *     these calls return HNM_ERR_STATE).  Rank 0 makes the id, the launcher
+ *     distributes its HNM_DIST_ID_BYTES bytes (any side channel), every rank
+ *     calls hnm_dist_init on a renderer created with the matching hnm_shard. */
+#define HNM_DIST_ID_BYTES 128u
+int hnm_dist_unique_id(uint8_t* id);
+int hnm_dist_init(hnm_renderer* r, const uint8_t* id, uint32_t rank, uint32_t num_ranks);
+/* Collective (every rank calls it, same order).  rgb8 == NULL: take part in
+ * the gather only, asynchronously.  rgb8 != NULL: also run `update_imgbuf`
+ * on the gathered image and return it (host, width*height*3). */
+int hnm_dist_resolve(hnm_renderer* r, uint32_t sampling, uint8_t* rgb8);
+/* Collective; rgb != NULL receives the gathered f64 buffer in image row order. */
+int hnm_dist_read_accum(hnm_renderer* r, double* rgb);
+
 /* ---- batch entry points (per-function parity) ---------- */
 
 typedef struct hnm_ray { hnm_vec3 origin, direction; } hnm_ray;
@@ -307,6 +357,12 @@ int hnm_material_bsdf_batch(int device, const double* in, uint32_t n, double* ou
 /* deterministic libm used by the device code (sin, cos, exp, pow, acos):
  * fn 0 sin, 1 cos, 2 exp, 3 pow(x,y), 4 acos ; y ignored unless pow */
 int hnm_math_batch(int device, int fn, const double* x, const double* y, uint32_t n, double* out);
+
+/* `Texture::sample` (src/texture.rs:29-63,108-114) of image `image` of the
+ * scene (-1: constant colour) times `tint[3]` at n (u, v) pairs -> n rgb triples */
+int hnm_texture_sample_batch(hnm_scene* scene, int32_t image, const double* tint, const double* uv, uint32_t n, double* rgb);
+/* `Skybox::sample` (src/scene.rs:295-319) for n directions (xyz) -> n rgb triples */
+int hnm_skybox_sample_batch(hnm_scene* scene, const double* directions, uint32_t n, double* rgb);
 
 #ifdef __cplusplus
 }

@@ -910,9 +910,20 @@ void oracle_render_paths(const hnm_scene_desc* d, const hnm_camera* camera, uint
 
 // `Renderer::render` (src/renderer.rs:25-46) for passes sampling_first .. +count-1 over image rows
 // [row_begin, row_end): accum (f64 rgb, full image, row 0 = top) += supersampling(...)
+// src/renderer.rs:25-46 restricted to the pixel rectangle [col_begin, col_end) x [row_begin, row_end) of the w x h image
+// (every pixel is independent: the rectangle's pixels get exactly the values a full render gives them)
+void oracle_render_rect(const hnm_scene_desc* d, const hnm_camera* camera, uint32_t w, uint32_t h, int mode, uint32_t sampling_first,
+                        uint32_t count, uint32_t col_begin, uint32_t col_end, uint32_t row_begin, uint32_t row_end, double* accum,
+                        oracle_counters* counters);
 void oracle_render(const hnm_scene_desc* d, const hnm_camera* camera, uint32_t w, uint32_t h, int mode, uint32_t sampling_first,
                    uint32_t count, uint32_t row_begin, uint32_t row_end, double* accum, oracle_counters* counters) {
+    oracle_render_rect(d, camera, w, h, mode, sampling_first, count, 0, w, row_begin, row_end, accum, counters);
+}
+void oracle_render_rect(const hnm_scene_desc* d, const hnm_camera* camera, uint32_t w, uint32_t h, int mode, uint32_t sampling_first,
+                        uint32_t count, uint32_t col_begin, uint32_t col_end, uint32_t row_begin, uint32_t row_end, double* accum,
+                        oracle_counters* counters) {
     Ctx c = make_ctx(d);
+    const uint32_t cw = col_end - col_begin;
     uint32_t ss = d->config.supersampling;
     Counters total;
     for (uint32_t sampling = sampling_first; sampling < sampling_first + count; sampling++) {
@@ -920,9 +931,10 @@ void oracle_render(const hnm_scene_desc* d, const hnm_camera* camera, uint32_t w
         {
             Counters local;
             tl_counters = counters ? &local : nullptr;
-#pragma omp for schedule(dynamic, 256)
-            for (int64_t i = (int64_t)row_begin * w; i < (int64_t)row_end * w; i++) {
-                uint32_t y = (uint32_t)(i / w), x = (uint32_t)(i - (int64_t)y * w);
+#pragma omp for schedule(dynamic, 16)
+            for (int64_t k = 0; k < (int64_t)(row_end - row_begin) * cw; k++) {
+                uint32_t y = row_begin + (uint32_t)(k / cw), x = col_begin + (uint32_t)(k % cw);
+                const int64_t i = (int64_t)y * w + x;
                 V3 accumulation = from_one(0.0);  // src/renderer.rs:49
                 for (uint32_t sy = 0; sy < ss; sy++)
                     for (uint32_t sx = 0; sx < ss; sx++) {

@@ -86,14 +86,15 @@ class Oracle:
                                      C.c_uint32(sampling), _vp(out), C.byref(cnt))
         return out, cnt.dict()
 
-    def render(self, host_scene, w, h, mode, sampling_first, count, accum=None, rows=None, camera=None, counters=True):
+    def render(self, host_scene, w, h, mode, sampling_first, count, accum=None, rows=None, camera=None, counters=True, cols=None):
         if accum is None:
             accum = np.zeros((h, w, 3), np.float64)
         r0, r1 = rows if rows else (0, h)
+        c0, c1 = cols if cols else (0, w)
         cnt = OracleCounters()
-        self.lib.oracle_render(host_scene.desc, camera or host_scene.camera, C.c_uint32(w), C.c_uint32(h), C.c_int(mode),
-                               C.c_uint32(sampling_first), C.c_uint32(count), C.c_uint32(r0), C.c_uint32(r1), _vp(accum),
-                               C.byref(cnt) if counters else None)
+        self.lib.oracle_render_rect(host_scene.desc, camera or host_scene.camera, C.c_uint32(w), C.c_uint32(h), C.c_int(mode),
+                                    C.c_uint32(sampling_first), C.c_uint32(count), C.c_uint32(c0), C.c_uint32(c1), C.c_uint32(r0),
+                                    C.c_uint32(r1), _vp(accum), C.byref(cnt) if counters else None)
         return accum, cnt.dict()
 
     def resolve(self, cfg, accum, sampling):

@@ -1,0 +1,237 @@
+"""Directed edge cases of the closest-hit path and of the texture / skybox lookups, CUDA vs oracle, every field bit-identical;
+and the whole-path parity test repeated under every run-time switch of the core.
+
+What random rays never reach: the reference tests a primitive only if EVERY f64 box on its chain
+passes `tmin <= tmax && !signbit(tmax)` (src/bvh.rs:20-39,214,240), NaN cases included -- an axis-parallel ray whose origin
+coordinate equals a box plane gives 0 * inf = NaN there.  The GPU traversal is conservative and decides by the exact
+primitive test, so these rays are where the two could disagree."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def scene_vertices(scene):
+    d = scene.desc.contents
+    v = np.ctypeslib.as_array(d.vertices, shape=(d.num_vertices * 3,)).reshape(-1, 3).copy()
+    f = np.ctypeslib.as_array(d.faces, shape=(d.num_faces * 3,)).reshape(-1, 3).copy()
+    # face vertex indices are relative to their mesh's vertex_offset
+    faces = []
+    for i in range(d.num_meshes):
+        m = d.meshes[i]
+        faces.append(f[m.face_offset:m.face_offset + m.face_count] + m.vertex_offset)
+    return v, np.concatenate(faces) if faces else np.zeros((0, 3), np.int64)
+
+
+def directed_rays(scene, rng, n_each=4000):
+    v, f = scene_vertices(scene)
+    cam = np.array(scene.camera.contents.eye.tuple())
+    pick = rng.integers(0, len(v), n_each)
+    P = v[pick]
+    O, D = [], []
+    # (a) axis-parallel rays THROUGH a vertex: two origin coordinates equal the vertex's (and with it the planes of every
+    #     box that vertex bounds), direction exactly +-e_k
+    for axis in range(3):
+        for sign in (1.0, -1.0):
+            o = P.copy()
+            o[:, axis] -= sign * 7.0
+            d = np.zeros_like(P)
+            d[:, axis] = sign
+            O.append(o); D.append(d)
+    # (b) axis-parallel rays that share ONE coordinate with a vertex (on a box plane, not through the vertex)
+    for axis in range(3):
+        o = P.copy()
+        o[:, axis] += 9.0
+        o[:, (axis + 1) % 3] += rng.normal(size=n_each) * 0.05
+        d = np.zeros_like(P)
+        d[:, axis] = -1.0
+        O.append(o); D.append(d)
+    # (c) one direction component exactly zero, origin coordinate on a box plane
+    for axis in range(3):
+        d = rng.normal(size=(n_each, 3))
+        d[:, axis] = 0.0
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        o = P - d * rng.uniform(1.0, 6.0, size=(n_each, 1))
+        O.append(o); D.append(d)
+    # (d) rays aimed at shared vertices from the camera and from random points
+    for src in (np.tile(cam, (n_each, 1)), rng.uniform(-4, 4, size=(n_each, 3)) * [1, 0.4, 1] + [0, 1.5, 0]):
+        d = P - src
+        nrm = np.linalg.norm(d, axis=1, keepdims=True)
+        ok = nrm[:, 0] > 1e-9
+        O.append(src[ok]); D.append(d[ok] / nrm[ok])
+    if len(f):
+        # (e) rays ALONG edges (inside the triangle's plane: the determinant is 0 up to rounding) and through edge midpoints
+        fi = f[rng.integers(0, len(f), n_each)]
+        a, b, c = v[fi[:, 0]], v[fi[:, 1]], v[fi[:, 2]]
+        e = b - a
+        ln = np.linalg.norm(e, axis=1, keepdims=True)
+        ok = ln[:, 0] > 1e-12
+        O.append((a - e * 3.0)[ok]); D.append((e / np.maximum(ln, 1e-300))[ok])
+        mid = 0.5 * (a + b)
+        d = mid - cam
+        O.append(np.tile(cam, (n_each, 1))); D.append(d / np.linalg.norm(d, axis=1, keepdims=True))
+        # (f) origins exactly ON a triangle (t = 0 is accepted by `t < 0.0` rejecting only negatives, src/bvh.rs:281) and at a vertex
+        onp = a + 0.25 * (b - a) + 0.25 * (c - a)
+        d = rng.normal(size=(n_each, 3))
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        O.append(onp); D.append(d)
+        O.append(a.copy()); D.append(d)
+    return np.concatenate(O), np.concatenate(D)
+
+
+@pytest.mark.parametrize("name", ["rtcamp6", "bvh_heavy", "diamond", "material_examples_pl"])
+def test_directed_rays_match_oracle(hr, core, oracle, get_scene, get_device_scene, name):
+    scene, dev = get_scene(name), get_device_scene(name)
+    rng = np.random.default_rng(21)
+    o, d = directed_rays(scene, rng)
+    got = dev.intersect(o, d)
+    want = oracle.intersect(scene, o, d)
+    bad = {}
+    for f in got.dtype.names:
+        g, w = got[f], want[f]
+        same = (bits(g) == bits(w)) if g.dtype == np.float64 else (g == w)
+        same = same.reshape(len(g), -1).all(axis=1)
+        if not same.all():
+            bad[f] = int((~same).sum())
+    assert not bad, (name, bad, len(o))
+    assert 0.02 < got["hit"].mean() < 1.0
+
+
+def test_rays_in_cuboid_face_planes(hr, core, oracle, get_scene, get_device_scene):
+    """Cuboid::intersect is the same slab test (src/scene.rs:152-155): rays that travel IN the plane of a face, start on a
+    face, or are axis-parallel through an edge."""
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    d = scene.desc.contents
+    cub = [d.elements[i] for i in range(d.num_elements) if d.elements[i].kind == 1]
+    assert cub
+    rng = np.random.default_rng(3)
+    O, D = [], []
+    for e in cub:
+        lo, hi = np.array(e.a.tuple()), np.array(e.b.tuple())
+        n = 3000
+        for axis in range(3):
+            for plane in (lo[axis], hi[axis]):
+                o = rng.uniform(lo - 2.0, hi + 2.0, size=(n, 3))
+                o[:, axis] = plane
+                dd = rng.normal(size=(n, 3))
+                dd[:, axis] = 0.0                      # in-plane
+                dd /= np.linalg.norm(dd, axis=1, keepdims=True)
+                O.append(o); D.append(dd)
+                dd2 = rng.normal(size=(n, 3))          # starting on the plane, leaving it
+                dd2 /= np.linalg.norm(dd2, axis=1, keepdims=True)
+                O.append(o.copy()); D.append(dd2)
+                dd3 = np.zeros((n, 3))
+                dd3[:, (axis + 1) % 3] = 1.0           # axis-parallel inside the plane
+                O.append(o.copy()); D.append(dd3)
+    o, dd = np.concatenate(O), np.concatenate(D)
+    got, want = dev.intersect(o, dd), oracle.intersect(scene, o, dd)
+    for f in got.dtype.names:
+        g, w = got[f], want[f]
+        assert (np.array_equal(bits(g), bits(w)) if g.dtype == np.float64 else np.array_equal(g, w)), f
+
+
+# ---------------------------------------------------------------------------------------- texture / skybox entry points
+def test_texture_sample_edge_cases(hr, core, oracle, get_scene, get_device_scene):
+    """`Texture::sample` (src/texture.rs:29-63,108-114): v = 1 (the `height - y - 1` u32 wrap clamps to the BOTTOM row),
+    u = 1 (clamp), u, v = 0, texel centres and boundaries, negative and > 1 coordinates (the `as u32` cast saturates),
+    NaN (-> 0), and a tint; every image of the scene."""
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    nimg = scene.desc.contents.num_images
+    rng = np.random.default_rng(5)
+    for image in list(range(nimg)) + [-1]:
+        w = scene.desc.contents.images[image].width if image >= 0 else 16
+        h = scene.desc.contents.images[image].height if image >= 0 else 16
+        uv = [rng.random((20000, 2))]
+        edge = np.array([0.0, 1.0, 1.0 - 2 ** -53, 0.5, 1.0 / w, 1.0 / h, 1.0 - 1.0 / w, 1.0 - 1.0 / h, 1.0 - 0.5 / h, 0.5 / w, -0.0, -0.25, 1.25, 2.0,
+                         1e300, -1e300, np.nan])
+        uu, vv = np.meshgrid(edge, edge)
+        uv.append(np.stack([uu.ravel(), vv.ravel()], axis=1))
+        k = np.arange(0, min(w, 512))
+        uv.append(np.stack([k / w, np.full(len(k), 1.0)], axis=1))            # exact texel boundaries along the top row
+        uv.append(np.stack([np.full(len(k), 1.0), k / h], axis=1))
+        uv = np.concatenate(uv)
+        tint = (0.5, 1.0, 0.25)
+        got = dev.texture_sample(image, tint, uv)
+        want = oracle.texture_sample(scene, image, tint, uv)
+        assert np.array_equal(bits(got), bits(want)), (image, int((bits(got) != bits(want)).any(axis=1).sum()))
+
+
+def test_skybox_sample_edge_cases(hr, core, oracle, get_scene, get_device_scene):
+    """`Skybox::sample` (src/scene.rs:295-319): face selection uses strict `>` (ties fall through to z), the sign tests see
+    -0.0 as negative, and u, v reach the face borders exactly."""
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    rng = np.random.default_rng(6)
+    d = [rng.normal(size=(50000, 3))]
+    vals = [1.0, -1.0, 0.0, -0.0, 0.5, -0.5, 1e-300, -1e-300]
+    grid = np.array([[a, b, c] for a in vals for b in vals for c in vals])
+    d.append(grid)                                   # every tie |x| == |y|, |y| == |z|, all-zero (0/0 = NaN), signed zeros
+    t = rng.normal(size=(20000, 3))
+    t[:, 1] = np.abs(t[:, 0]) * np.sign(t[:, 1])     # |x| == |y| ties with random signs
+    d.append(t)
+    t = rng.normal(size=(20000, 3))
+    t[:, 2] = t[:, 0]
+    d.append(t)
+    d = np.concatenate(d)
+    got = dev.skybox_sample(d)
+    want = oracle.skybox_sample(scene, d)
+    assert np.array_equal(bits(got), bits(want)), int((bits(got) != bits(want)).any(axis=1).sum())
+
+
+# ---------------------------------------------------------------------------------------- run-time switches
+@pytest.mark.parametrize("env", [{"HNM_BVH": "ref"}, {"HNM_SHADOW_BOUNDED": "0"}, {"HNM_RNG_OVERLAP": "0"}, {"HNM_RNG_SPECULATE": "0"},
+                                 {"HNM_RNG_START_BOUNCE": "0"}, {"HNM_RNG_START_BOUNCE": "3"}, {"HNM_TRACE_BLOCKS": "5"},
+                                 {"HNM_GRAPH": "0"}, {"HNM_BVH": "ref", "HNM_SHADOW_BOUNDED": "0", "HNM_RNG_OVERLAP": "0"}])
+def test_switches_do_not_change_bits(hr, core, oracle, get_scene, monkeypatch, env):
+    """Every switch DESIGN.md names only changes HOW the same result is computed: the reference's median-split topology
+    instead of the SAH tree, unbounded shadow queries, no generation/trace overlap, no speculative generation."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name, w, h, first, count in (("rtcamp6", 200, 113, 1, 4), ("simple_pl", 120, 68, 2, 2), ("diamond", 120, 68, 1, 2)):
+        scene = get_scene(name)
+        dev = hr.DeviceScene(scene, 0)   # HNM_BVH is read by hnm_scene_create: a fresh device scene, not the cached one
+        ctx = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING, max_batch=2)
+        ctx.render_passes(first, count)
+        ctx.render_passes(first + count, 1)
+        ctx.synchronize()
+        got = ctx.read_accum()
+        c = ctx.counters()
+        ctx.close()
+        dev.close()
+        want, cnt = oracle.render(scene, w, h, hr.MODE_PATHTRACING, first, count + 1)
+        assert np.array_equal(bits(got), bits(want)), (env, name, int((got != want).any(axis=2).sum()))
+        assert (c["segments"], c["shadow_rays"]) == (cnt["segments"], cnt["shadow_rays"])
+
+
+@pytest.mark.parametrize("bounce_limit", [2, 3, 17])
+def test_bounce_limit_range(hr, core, oracle, get_scene, bounce_limit):
+    """config.bounce_limit crosses the ABI (src/config.rs:14 is 10).  17 is the largest accepted value: every path then
+    needs all 32 stored words of its random stream after the lens loop, so any path with more than ... takes the exact slow
+    path (18 and above used to read past the stored tail; now rejected by hnm_scene_create)."""
+    import copy
+    import ctypes as C
+    from hanamaru_renderer_b200 import _ffi
+    scene = get_scene("material_examples_pl")
+    old = scene.desc.contents.config.bounce_limit
+    scene.desc.contents.config.bounce_limit = bounce_limit
+    try:
+        dev = hr.DeviceScene(scene, 0)
+        w, h = 96, 54
+        ctx = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING)
+        ctx.render_passes(1, 2)
+        ctx.synchronize()
+        got = ctx.read_accum()
+        c = ctx.counters()
+        ctx.close()
+        dev.close()
+        want, cnt = oracle.render(scene, w, h, hr.MODE_PATHTRACING, 1, 2)
+        assert np.array_equal(bits(got), bits(want)), bounce_limit
+        assert (c["segments"], c["shadow_rays"]) == (cnt["segments"], cnt["shadow_rays"])
+        if bounce_limit == 17:
+            assert c["rng_fallbacks"] == c["paths"]     # 2 + 32 words needed, 32 stored: everyone takes the slow path
+    finally:
+        scene.desc.contents.config.bounce_limit = old
+    del copy, C, _ffi

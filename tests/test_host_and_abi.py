@@ -233,8 +233,10 @@ def test_no_cpu_fallback_without_device(hr):
     """Without a GPU every compute entry point fails loudly; nothing routes to the oracle."""
     import __graft_entry__ as g
     g.build_core()
-    if hr.device_count() > 0:
+    if hr.device_count_or_zero() > 0:
         pytest.skip("a CUDA device is present")
+    with pytest.raises(hr.HanamaruError):
+        hr.device_count()          # a driver error is reported, not read as "0 devices"
     assets = hr.AssetStore.from_pack()
     scene = hr.build_scene("diamond", assets)
     with pytest.raises(hr.HanamaruError):
@@ -280,4 +282,15 @@ def test_scene_validation_rejects_malformed(hr, get_scene):
     bad.num_elements = 0
     assert core.hnm_scene_create(C.byref(bad), 0, C.byref(h)) == -1
     assert core.hnm_scene_create(None, 0, C.byref(h)) == -1
+    # bounce_limit: 2 * (bounce_limit - 1) words of the per-path random stream must fit the stored tail (HNM_RNG_TAIL = 32)
+    for bl, ok in ((1, False), (18, False), (64, False)):
+        C.memmove(C.byref(bad), C.byref(src), C.sizeof(bad))
+        bad.config.bounce_limit = bl
+        assert core.hnm_scene_create(C.byref(bad), 0, C.byref(h)) == -1, bl
+        assert b"bounce_limit" in core.hnm_last_error()
+    # the group entry point validates the same way, before touching any device
+    devs = (C.c_int * 1)(0)
+    C.memmove(C.byref(bad), C.byref(src), C.sizeof(bad))
+    bad.config.bounce_limit = 18
+    assert core.hnm_group_create(C.byref(bad), get_scene("diamond").camera, 16, 16, 0, 1, devs, 0, 0, C.byref(h)) == -1
     del copy
