@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- Msamples/s of the radiance loop on the rtcamp6 scene at 1920x1080 (BASELINE.json).
+"""bench.py -- Msamples/s of the radiance loop (BASELINE.json), per config.
 
-  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
-  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path on the host cores
+  python bench.py --gpus N --steps K --warmup W [--config C]     the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...         the reference's CPU path on the host cores
 
 sample = one camera path = one `PathTracingRenderer::calc_pixel` call (src/renderer.rs:163).
-step   = PASSES_PER_STEP passes of the pass loop (src/renderer.rs:32-38) over the whole image; the job is
-         K steps (default 16 x 16 = 256 passes = BASELINE config 2) followed by ONE all-gather (N > 1) and one
-         resolve (`update_imgbuf`), all inside the timed region.
+config = BASELINE.json `configs` (1-origin): 2 (default) rtcamp6 1920x1080 x 256 passes; 3 BVH-heavy 75 k triangles
+         1920x1080 x 1024; 4 diamond (DoF + GGX-refraction) 1920x1080 x 4096; 5 rtcamp6 3840x2160 x 4096 (8 GPUs);
+         1 rtcamp6 480x270 x 1.  The pass count of a config is K steps x its passes per step.
+step   = passes-per-step passes of the pass loop (src/renderer.rs:32-38) over the whole image; the job is K steps
+         followed by ONE gather (N > 1) and one resolve (`update_imgbuf`), all inside the timed region.
 value  = samples of the whole job / device time (CUDA events on the renderer's stream, max over ranks); the
          scene is resident in HBM when the timed region starts.
-e2e    = the same job through the reference-facing call PathTracingRenderer.render(scene, camera, imgbuf)
-         with HOST buffers: scene upload from host memory, passes, a progress image resolved and copied
-         back to the host every step, wall clock.
-N > 1  : one process per GPU (torchrun), interleaved row tiles, fixed total work -> "strong" scaling.
+e2e    = the same job through the C ABI with HOST buffers: scene upload from host memory, passes, a progress
+         image resolved and copied back to the host every step, wall clock.
+N > 1  : one process per GPU (torchrun), interleaved row tiles, fixed total work -> "strong" scaling; the gather is the
+         C ABI's own ncclAllGather (hnm_dist_*), torch.distributed only carries the unique id, barriers and max-over-ranks.
+reference arm: the oracle port (glibc flavour, OpenMP on all host threads) renders the SAME scene at the SAME size,
+         whole image, one pass per step.
 """
 import argparse
 import json
@@ -27,11 +31,25 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT = 1920, 1080
-SCENE = "rtcamp6"
-PASSES_PER_STEP = 16
-METRIC = "Msamples/sec (rtcamp6 scene, 1920x1080)"
 UNIT = "Msamples/s"
+# BASELINE.json configs (1-origin).  steps x pps = the config's pass count with the default --steps 16.
+CONFIGS = {
+    1: dict(scene="rtcamp6", w=480, h=270, pps=1, name="rtcamp6 default scene 480x270 (BASELINE config 1)"),
+    2: dict(scene="rtcamp6", w=1920, h=1080, pps=16, name="rtcamp6 default scene 1920x1080 (BASELINE config 2), GGX + NEE + IBL"),
+    3: dict(scene="bvh_heavy", w=1920, h=1080, pps=64, name="BVH-heavy mesh scene 1920x1080 (BASELINE config 3): default scene + "
+                                                              "fractal_icosahedron + fractal_dodecahedron, 75 k triangles"),
+    4: dict(scene="diamond", w=1920, h=1080, pps=256, name="DoF + GGX-refraction diamond scene 1920x1080 (BASELINE config 4)"),
+    5: dict(scene="rtcamp6", w=3840, h=2160, pps=256, name="rtcamp6 default scene 3840x2160 (BASELINE config 5), tile-sharded"),
+}
+
+
+def metric_name(cfg):
+    return "Msamples/sec (%s scene, %dx%d)" % (cfg["scene"], cfg["w"], cfg["h"])
+
+
+def workload(cfg):
+    """The same string in both arms: what is rendered, not how much of it one step covers."""
+    return "%s; f64, 4 sub-pixel paths per pixel and pass" % cfg["name"]
 
 
 def load_peaks():
@@ -101,27 +119,20 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_reference_run(oracle, scene, hr, steps, warmup, tile_stride=4):
-    """The reference's CPU path (oracle port, glibc libm, OpenMP over pixels like rayon's par_iter_mut) on a bounded
-    sample of the same workload: one pass over every `tile_stride`-th 8-row tile of the 1920x1080 image per step."""
+def cpu_reference_run(oracle, scene, hr, cfg, steps, warmup):
+    """The reference's CPU path (oracle port, glibc libm, OpenMP over pixels like rayon's par_iter_mut): one pass over the
+    WHOLE image of the config per step -- the same scene, resolution and per-pass work as the GPU arm."""
     import numpy as np
-    rows = [(y, min(y + 8, HEIGHT)) for y in range(0, HEIGHT, 8 * tile_stride)]
-    nrows = sum(b - a for a, b in rows)
-    accum = np.zeros((HEIGHT, WIDTH, 3), np.float64)
-
-    def one_step(sampling):
-        for a, b in rows:
-            oracle.render(scene, WIDTH, HEIGHT, hr.MODE_PATHTRACING, sampling, 1, accum=accum, rows=(a, b), counters=False)
-
+    W, H = cfg["w"], cfg["h"]
+    accum = np.zeros((H, W, 3), np.float64)
     for i in range(warmup):
-        one_step(1 + i)
+        oracle.render(scene, W, H, hr.MODE_PATHTRACING, 1 + i, 1, accum=accum, counters=False)
     t0 = time.perf_counter()
     for i in range(steps):
-        one_step(1 + warmup + i)
+        oracle.render(scene, W, H, hr.MODE_PATHTRACING, 1 + warmup + i, 1, accum=accum, counters=False)
     dt = time.perf_counter() - t0
-    samples = nrows * WIDTH * 4 * steps
-    sample_desc = "%d passes over every %dth 8-row tile of the %dx%d image (%d rows, %.2f Msamples per step)" % (
-        steps, tile_stride, WIDTH, HEIGHT, nrows, nrows * WIDTH * 4 / 1e6)
+    samples = W * H * 4 * steps
+    sample_desc = "%d whole-image passes of %dx%d (%.2f Msamples per step)" % (steps, W, H, W * H * 4 / 1e6)
     return samples / dt / 1e6, dt, sample_desc
 
 
@@ -129,6 +140,7 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0  # rank 0 alone runs the CPU arm
+    cfg = CONFIGS[args.config]
     # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all host threads (it is the only
     # process doing work), so undo that before the OpenMP runtime of the oracle library initialises
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
@@ -136,22 +148,71 @@ def run_reference(args):
     import hanamaru_renderer_b200 as hr
     from oracle_ffi import Oracle  # the one other place bench.py may execute oracle/
     oracle = Oracle("glibc")
-    scene = hr.build_scene(SCENE, hr.AssetStore.from_pack())
+    scene = hr.build_scene(cfg["scene"], hr.AssetStore.from_pack())
     cores = os.cpu_count()
-    value, dt, sample = cpu_reference_run(oracle, scene, hr, args.steps, args.warmup)
+    value, dt, sample = cpu_reference_run(oracle, scene, hr, cfg, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (in-repo rtcamp6 scene from assets/hanamaru_assets.hnmpack)",
-        "config": {"workload": "rtcamp6 default scene 1920x1080 (BASELINE config 2), CPU sample per step: see cpu_baseline.sample"},
+        "data": "synthetic (in-repo scene from assets/hanamaru_assets.hnmpack; seeds fixed by the algorithm)",
+        "config": {"workload": workload(cfg), "config": args.config},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample + "; oracle/liboracle.so = f64 C++ restatement of the Rust hot path (the Rust "
-                                            "reference cannot be built here: no cargo/rustc), OpenMP on all host threads"},
+                                            "reference cannot be built here: no cargo/rustc), OpenMP on all host threads; the "
+                                            "restatement reproduces the reference's published 1000x4spp image to +-1 u8 level"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def measure_traffic(cfg, top):
+    """dram__bytes_read + dram__bytes_write of the dominant kernel, measured NOW: one pass of this config under
+    `ncu --metrics dram__bytes...` (tools/traffic_probe.py).  Returns bytes per launch of the probe and its units, or None."""
+    ncu = "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    kname = {"isaac_raygen": "k_isaac_raygen", "trace": "k_trace", "confirm": "k_confirm", "shade_nee": "k_shade_surf",
+             "shade_delta": "k_shade_surf", "shade_miss": "k_shade_miss", "nee_resolve": "k_nee_resolve"}.get(top)
+    if not kname:
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--kernel-name", "regex:" + kname,
+           "--launch-count", "3", "--csv", sys.executable, os.path.join(ROOT, "tools", "traffic_probe.py"), cfg["scene"], str(cfg["w"]), str(cfg["h"])]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, HNM_RNG_OVERLAP="0")).stdout
+    except Exception:
+        return None
+    import csv
+    rows = [r for r in csv.reader(out.splitlines()) if len(r) > 5]
+    if not rows:
+        return None
+    hdr = None
+    per_launch = {}
+    for r in rows:
+        if "Metric Name" in r and "Metric Value" in r:
+            hdr = r
+            continue
+        if not hdr or len(r) != len(hdr):
+            continue
+        d = dict(zip(hdr, r))
+        name = d.get("Kernel Name", "")
+        if top == "shade_nee" and "true" not in name and "<1>" not in name and "(bool)1" not in name:
+            continue
+        if top == "shade_delta" and ("true" in name or "<1>" in name or "(bool)1" in name):
+            continue
+        try:
+            v = float(d["Metric Value"].replace(",", ""))
+        except ValueError:
+            continue
+        unit = d.get("Metric Unit", "byte").lower()
+        v *= {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "tbyte": 1e12}.get(unit, 1.0)
+        per_launch.setdefault(d.get("ID", "0"), 0.0)
+        per_launch[d.get("ID", "0")] += v
+    if not per_launch:
+        return None
+    first = sorted(per_launch.items(), key=lambda kv: int(kv[0]) if kv[0].isdigit() else 0)[0][1]
+    return first  # the first launch of that kernel in the probe = the first-bounce / whole-pass launch
 
 
 def run_ours(args):
@@ -160,6 +221,8 @@ def run_ours(args):
     if world != args.gpus:
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch N > 1 with torchrun (one process per GPU)")
+    cfg = CONFIGS[args.config]
+    WIDTH, HEIGHT = cfg["w"], cfg["h"]
     import hanamaru_renderer_b200 as hr
     from hanamaru_renderer_b200 import dist as hd
     if hr.device_count() < 1:
@@ -176,23 +239,36 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def share_unique_id():
+        """rank 0 makes the NCCL id of the C ABI's own communicator; torch.distributed is the side channel"""
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t.copy_(torch.tensor(list(hr.dist_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().tolist())
+
     assets = hr.AssetStore.from_pack()
-    scene = hr.build_scene(SCENE, assets)
+    scene = hr.build_scene(cfg["scene"], assets)
     dev = hr.DeviceScene(scene, local)
     tile_rows = int(os.environ.get("HNM_TILE_ROWS", hd.DEFAULT_TILE_ROWS))
     shard = (rank, world, tile_rows) if use_dist else None
     ctx = hr.RenderContext(dev, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
-    P = args.pps
+    if use_dist:
+        ctx.dist_init(share_unique_id(), rank, world)
+    P = args.pps or cfg["pps"]
     K, Wm = args.steps, args.warmup
+
+    def resolve(c, sampling, out=None):
+        """update_imgbuf of the whole image: rank 0 gets it; N > 1 = ncclAllGather of the shards inside the C ABI"""
+        if use_dist:
+            return c.dist_resolve(sampling, out=out, want_image=(rank == 0))
+        return c.resolve(sampling, out=out)
 
     # ---- warm-up (untimed) -----------------------------------------------------------------------------
     for i in range(Wm):
         ctx.render_passes(1 + i * P, P)
     ctx.synchronize()
-    if use_dist:
-        hd.gather_and_resolve(ctx, Wm * P)
-    else:
-        ctx.resolve(max(Wm * P, 1))
+    resolve(ctx, max(Wm * P, 1))
     ctx.clear()
     ctx.synchronize()
 
@@ -205,10 +281,7 @@ def run_ours(args):
     for i in range(K):
         ctx.render_passes(1 + i * P, P)
     ctx.mark(1)
-    if use_dist:
-        img, _ = hd.gather_and_resolve(ctx, K * P)
-    else:
-        img = ctx.resolve(K * P)
+    img = resolve(ctx, K * P)
     ctx.mark(2)
     ctx.synchronize()
     barrier()
@@ -233,9 +306,8 @@ def run_ours(args):
     ctx.clear()
     ctx.synchronize()
     ctx.set_profiling(True)
-    prof_steps = min(K, 2)
-    for i in range(prof_steps):
-        ctx.render_passes(1 + i * P, P)
+    prof_passes = min(K * P, max(P, 2 * 16))
+    ctx.render_passes(1, prof_passes)
     ctx.synchronize()
     ktimes = ctx.kernel_times()
     pc = ctx.counters()
@@ -243,13 +315,14 @@ def run_ours(args):
     peak, peak_src = load_peaks()
     roofline = None
     kernel_share = {}
+    nl_scene = max(1, scene.desc.contents.num_emissions)
     if ktimes:
         tot = sum(v[0] for v in ktimes.values())
         kernel_share = {k: round(v[0] / tot, 4) for k, v in ktimes.items()}
         top = max(ktimes, key=lambda k: ktimes[k][0])
         paths_p = pc["paths"]
-        seg, sh = pc["segments"], pc["shadow_rays"]
-        nee_events = sh / max(1, scene.desc.contents.num_emissions)
+        seg, sh = pc["segments"], pc["shadow_rays"]      # S and N of THIS run, counted on the device
+        nee_events = sh / nl_scene
         # algorithmic HBM bytes per unit (the records actually shipped):
         #   isaac    : write 32-word tail 256 + first-bounce ray 76 + L 24 + cursor 1                = 357 B / path
         #   trace    : read origin + direction 48 (+ 4 tmax for shadow rays); write list header 8 + 8 per candidate
@@ -257,49 +330,44 @@ def run_ours(args):
         #   confirm  : camera rays: read ray 48 + header 8 + 8 per candidate; write hit 32 + queue entry 4; the f64
         #              triangles it tests come from the L2-resident scene (shadow rays: inside nee_resolve) = 101 B per ray
         #   shade_nee: read queue 4 + ray 48 + thr 24 + pid 4 + hit 32 + rng 17; write next ray 76 (survivors; counted
-        #              for all) + event 76 + shadow ray 92                                           = 373 B / NEE event
+        #              for all) + event 76 + 92 per shadow ray                                       = 281 + 92 L B / NEE event
         cand = 1.1
         per_unit = {"trace": ((56.0 + 8 * cand) * seg / max(1, seg + sh) + (60.0 + 8 * cand) * sh / max(1, seg + sh), seg + sh),
                     "confirm": (92.0 + 8 * cand, seg),
-                    "shade_nee": (373.0, nee_events),
+                    "shade_nee": (281.0 + 92.0 * nl_scene, nee_events),
                     "isaac_raygen": (357.0, paths_p), "shade_miss": (4 + 24 + 24 + 4 + 48.0, paths_p),
-                    "shade_delta": (4 + 48 + 24 + 4 + 32 + 17 + 48 + 76.0, seg - nee_events)}
+                    "shade_delta": (4 + 48 + 24 + 4 + 32 + 17 + 48 + 76.0, seg - nee_events),
+                    "nee_resolve": (108.0 + 92.0 * nl_scene + 8 * cand * nl_scene, nee_events)}
         if top in per_unit:
             b, units = per_unit[top]
             ms, nl = ktimes[top]
             achieved = b * units / (ms * 1e-3) / 1e9
-            traffic = None
-            tp = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tp):
-                try:
-                    traffic = json.load(open(tp)).get(top)
-                except Exception:
-                    traffic = None
             roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": traffic, "peak_source": peak_src, "launches": nl, "avg_launch_ms": ms / nl,
+                        "traffic": None, "peak_source": peak_src, "launches": nl, "avg_launch_ms": ms / nl,
                         "algorithmic_bytes_per_unit": b, "units_per_launch": units / nl,
-                        "note": "not HBM bound by construction: the scene (<= 70 MB) is L2 resident and HBM only carries the wavefront records; "
+                        "segments_per_sample": seg / max(1, paths_p), "shadow_rays_per_sample": sh / max(1, paths_p),
+                        "note": "not HBM bound by construction: the scene is L2 resident and HBM only carries the wavefront records; "
                                 "ISAAC-64 seeding is ALU-latency bound at 112 paths (224 KB of shared-memory state) per SM, "
-                                "k_trace is issue bound (77 % issue-slot utilisation, profiles/)"}
+                                "k_trace is issue bound (profiles/)"}
 
-    # ---- end-to-end through the reference-facing call, host buffers, wall clock -----------------------------
+    # ---- end-to-end through the C ABI, host buffers, wall clock ----------------------------------------------
     # (the device-timed renderer is released first: a second 25 GB arena next to a live one makes cudaMalloc 4x slower)
     ctx.close()
     ctx = None
     e2e = None
     if not args.no_e2e:
+        uid = share_unique_id() if use_dist else None   # side channel, outside the timed region like the launcher's rendezvous
         barrier()
         imgbuf = np.zeros((HEIGHT, WIDTH, 3), np.uint8)
         scene_bytes = scene_host_bytes(scene)
         t0 = time.perf_counter()
         dev2 = hr.DeviceScene(scene, local)                       # H2D: the flat scene description (host arrays)
         ctx2 = hr.RenderContext(dev2, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
+        if use_dist:
+            ctx2.dist_init(uid, rank, world)
         for i in range(K):
             ctx2.render_passes(1 + i * P, P)
-            if use_dist:
-                imgbuf[:], _ = hd.gather_and_resolve(ctx2, (i + 1) * P)   # progress image every step: NCCL gather + resolve + D2H
-            else:
-                ctx2.resolve((i + 1) * P, out=imgbuf)             # D2H: the resolved u8 image
+            resolve(ctx2, (i + 1) * P, out=imgbuf)                # progress image every step: (gather +) resolve + D2H on rank 0
         ctx2.synchronize()
         barrier()
         dt = time.perf_counter() - t0
@@ -312,31 +380,47 @@ def run_ours(args):
         e2e = {"value": samples / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": scene_bytes // K, "d2h_bytes_per_step": WIDTH * HEIGHT * 3,
                "seconds": dt, "includes": "scene upload from host memory (once), %d passes, a resolved progress image copied to the host every step" % (K * P)}
 
+    # ---- DRAM traffic of the dominant kernel, measured now (ncu, one pass of this config); N = 1 only -----------------
+    if roofline and rank == 0 and world == 1 and not args.no_traffic:
+        dev.close()
+        probe = measure_traffic(cfg, roofline["kernel"])
+        if probe is not None:
+            # the probe launch processes one pass: scale to the bench's units per launch
+            units_probe = {"isaac_raygen": WIDTH * HEIGHT * 4, "trace": WIDTH * HEIGHT * 4, "confirm": WIDTH * HEIGHT * 4,
+                           "shade_miss": None, "shade_nee": None, "shade_delta": None, "nee_resolve": None}.get(roofline["kernel"])
+            roofline["traffic_probe"] = {"bytes_per_launch": probe, "how": "ncu dram__bytes_read.sum + dram__bytes_write.sum, first launch of the kernel "
+                                         "in one %dx%d pass (tools/traffic_probe.py), measured in this run" % (WIDTH, HEIGHT), "units": units_probe}
+            if units_probe:
+                roofline["traffic"] = probe / units_probe * roofline["units_per_launch"]
+                roofline["traffic_bytes_per_unit"] = probe / units_probe
+
     # ---- CPU baseline beside it (rank 0, N = 1 only): bounded sample of the same workload ------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from oracle_ffi import Oracle  # checker / baseline only -- never on the product path
-        v, dt, sample = cpu_reference_run(Oracle("glibc"), scene, hr, steps=6, warmup=1)
+        v, dt, sample = cpu_reference_run(Oracle("glibc"), scene, hr, cfg, steps=2, warmup=0)
         cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                "sample": sample + "; f64 C++ restatement (oracle/), OpenMP on all host threads; the Rust reference cannot be built here"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "metric": metric_name(cfg), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic (in-repo rtcamp6 scene from assets/hanamaru_assets.hnmpack; seeds fixed by the algorithm)",
-            "config": {"workload": "rtcamp6 default scene 1920x1080, %d passes x 4 spp (BASELINE config 2), GGX + NEE + IBL, f64 parity mode" % (K * P),
-                       "passes_per_step": P, "resolve": "one all-gather (N>1) + one update_imgbuf inside the timed region",
+            "dtype": "f64", "data": "synthetic (in-repo scene from assets/hanamaru_assets.hnmpack; seeds fixed by the algorithm)",
+            "config": {"workload": workload(cfg), "config": args.config, "passes": K * P,
+                       "passes_per_step": P, "resolve": "one gather (N>1: ncclAllGather inside the C ABI) + one update_imgbuf inside the timed region",
                        "l2": "wavefront records per step (>= 4 GB at N=1) are far larger than L2; no explicit flush",
-                       "parallelism": "interleaved 8-row tiles over %d rank(s), no data-path collective" % world,
+                       "parallelism": "interleaved %d-row tiles over %d rank(s), no data-path collective" % (tile_rows, world),
                        "passes_in_flight": "auto" if not args.batch else args.batch},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"ms_passes": ms_passes, "ms_total": ms_total, "wall_s": wall,
                        "segments_per_sample": counters["segments"] / samples, "shadow_rays_per_sample": counters["shadow_rays"] / samples,
                        "Mrays_per_s": (counters["segments"] + counters["shadow_rays"]) / (ms_total * 1e-3) / 1e6,
-                       "kernel_time_share": kernel_share, "image_mean": float(np.asarray(img).mean())},
+                       "kernel_time_share": kernel_share, "kernel_ms": {k: round(v[0], 3) for k, v in ktimes.items()},
+                       "profiled_passes": prof_passes,
+                       "image_mean": float(np.asarray(img).mean()) if img is not None else None},
         }
         print(json.dumps(line))
     if use_dist:
@@ -356,31 +440,53 @@ def scene_host_bytes(scene):
     return int(n)
 
 
+def build_stamp():
+    """sha of the sources the libraries are built from: ranks other than 0 wait until rank 0's build carries it"""
+    import hashlib
+    import __graft_entry__ as g
+    h = hashlib.sha256()
+    for path in sorted(g._sources(g.CSRC, (".cu", ".cuh", ".h", ".cpp")) + [os.path.join(ROOT, "include", "hanamaru_b200.h")]):
+        h.update(open(path, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-origin); 2 = the metric's own")
     ap.add_argument("--batch", type=int, default=0, help="passes in flight per wavefront (0 = auto)")
-    ap.add_argument("--pps", type=int, default=PASSES_PER_STEP, help="passes per step (profiling runs use a small value)")
+    ap.add_argument("--pps", type=int, default=0, help="passes per step (0 = the config's; profiling runs use a small value)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-traffic", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: W >= 3
     import __graft_entry__ as g
     rank, world, _ = dist_env()
+    stamp_path = os.path.join(ROOT, "hanamaru_renderer_b200", ".build_stamp")
+    stamp = build_stamp()
     if rank == 0:
         g.build_host()
         g.build_core()
         g.build_oracle()
+        with open(stamp_path + ".tmp", "w") as f:
+            f.write(stamp)
+        os.replace(stamp_path + ".tmp", stamp_path)
     else:
-        # rank 0 builds (a no-op when the in-tree libraries are current; the swap is atomic); the others only need the files to exist
-        libs = [os.path.join(ROOT, "hanamaru_renderer_b200", n) for n in ("libhanamaru_host.so", "libhanamaru_b200.so")]
+        # rank 0 builds (a no-op when the in-tree libraries are current; the swap is atomic).  The others wait for the stamp of
+        # THESE sources, so that no rank loads a stale library while rank 0 is still rebuilding.
         t0 = time.time()
-        while not all(os.path.exists(p) for p in libs) and time.time() - t0 < 600:
-            time.sleep(1.0)
+        while time.time() - t0 < 900:
+            try:
+                if open(stamp_path).read().strip() == stamp:
+                    break
+            except OSError:
+                pass
+            time.sleep(0.5)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -20,6 +20,7 @@ from ._ffi import (MODE_DEBUG_DEPTH, MODE_DEBUG_FOCALPLANE, MODE_DEBUG_NORMAL, M
 
 REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULT_PACK = os.path.join(REPO_ROOT, "assets", "hanamaru_assets.hnmpack")
+CUBEMAP_PACK = os.path.join(REPO_ROOT, "assets", "hanamaru_cubemaps.hnmpack")  # JPEG files, decoded by the C++ host on first use
 
 
 class HanamaruError(RuntimeError):
@@ -54,9 +55,12 @@ class AssetStore:
             pass
 
     @classmethod
-    def from_pack(cls, path=DEFAULT_PACK):
+    def from_pack(cls, path=DEFAULT_PACK, extra=(CUBEMAP_PACK,)):
         s = cls()
         _check_host(_ffi.host().hnmh_assets_load_pack(s._h, path.encode()) == 0)
+        for p in extra:
+            if os.path.exists(p):
+                _check_host(_ffi.host().hnmh_assets_load_pack(s._h, p.encode()) == 0)
         return s
 
     @classmethod
@@ -313,6 +317,11 @@ class RenderContext:
         _check(_ffi.core().hnm_get_counters(self._h, C.byref(c)))
         return {k: getattr(c, k) for k, _ in c._fields_}
 
+    def warp_slots(self):
+        m = (C.c_uint64 * 4)()
+        _check(_ffi.core().hnm_debug_warp_slots(self._h, m, 4))
+        return [int(x) for x in m]
+
     def set_profiling(self, on):
         _check(_ffi.core().hnm_set_profiling(self._h, int(on)))
 
@@ -523,6 +532,32 @@ def host_render(scene, mode, width, height, sampling=1, time_limit_sec=1e9, repo
     if rc != 0:
         raise HanamaruError(_ffi.host().hnmh_last_error().decode())
     return img, done.value
+
+
+def host_render_to_files(scene, mode, width, height, out_dir, sampling=1, time_limit_sec=1e9, report_interval_sec=1e9, passes_per_call=0, device=0):
+    """host_render + the reference's file outputs: NNN.png progress images and result.png, encoded by the C++ host."""
+    img = np.zeros((height, width, 3), np.uint8)
+    done = C.c_uint32(0)
+    rc = _ffi.host().hnmh_render_to_files(scene._h, int(mode), width, height, sampling, float(time_limit_sec), float(report_interval_sec),
+                                          passes_per_call, device, str(out_dir).encode(), _vp(img), C.byref(done))
+    if rc != 0:
+        raise HanamaruError(_ffi.host().hnmh_last_error().decode())
+    return img, done.value
+
+
+def image_decode(data):
+    """The C++ host's `image::open` (PNG, baseline JPEG) on bytes -> uint8 [H][W][4]."""
+    buf = (C.c_uint8 * len(data)).from_buffer_copy(data)
+    w, h = C.c_uint32(), C.c_uint32()
+    _check_host(_ffi.host().hnmh_image_decode(buf, len(data), C.byref(w), C.byref(h), None) == 0)
+    out = np.empty((h.value, w.value, 4), np.uint8)
+    _check_host(_ffi.host().hnmh_image_decode(buf, len(data), C.byref(w), C.byref(h), _vp(out)) == 0)
+    return out
+
+
+def save_png(path, rgb):
+    rgb = np.ascontiguousarray(rgb, np.uint8)
+    _check_host(_ffi.host().hnmh_save_png(str(path).encode(), _vp(rgb), rgb.shape[1], rgb.shape[0]) == 0)
 
 
 # --------------------------------------------------------------------------- batch entry points

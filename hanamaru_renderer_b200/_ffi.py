@@ -92,7 +92,7 @@ class Shard(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("segments", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("rng_fallbacks", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64)]
+                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("cand_overflows", C.c_uint64)]
 
 
 class Ray(C.Structure):
@@ -134,6 +134,7 @@ CORE_SYMBOLS = {
     "hnm_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "hnm_get_kernel_times": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hnm_set_profiling": (C.c_int, [_P, C.c_int]),
+    "hnm_debug_warp_slots": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint32]),
     "hnm_mark": (C.c_int, [_P, C.c_uint32]),
     "hnm_elapsed_ms": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "hnm_intersect_batch": (C.c_int, [_P, _P, C.c_uint32, _P]),
@@ -177,6 +178,10 @@ HOST_SYMBOLS = {
     "hnmh_scene_camera": (C.POINTER(Camera), [_P]),
     "hnmh_scene_destroy": (None, [_P]),
     "hnmh_render": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_int, _P, C.POINTER(C.c_uint32)]),
+    "hnmh_image_decode": (C.c_int, [_P, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _P]),
+    "hnmh_save_png": (C.c_int, [C.c_char_p, _P, C.c_uint32, C.c_uint32]),
+    "hnmh_render_to_files": (C.c_int, [_P, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_char_p, _P,
+                                       C.POINTER(C.c_uint32)]),
     "hnmh_stdrng": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_double, C.c_double, _P]),
     "hnmh_builder_create": (_P, []),
     "hnmh_builder_destroy": (None, [_P]),

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -57,7 +58,8 @@ struct hnm_renderer {
     double *tmp0 = nullptr, *tmp1 = nullptr;
     uint8_t* rgb8 = nullptr;
     uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
-    bool profiling = false, trace_stats = false, per_bounce_names = false;
+    bool profiling = false, trace_stats = false, per_bounce_names = false, wid_stats = false;
+    bool rng_midtrace = false;     // HNM_RNG_MIDTRACE=1: the prefetch is enqueued right behind a trace launch, without waiting for it
     uint64_t launches = 0;
     KernelTimer timer;
     double* ray_buf[2][6] = {};
@@ -91,6 +93,7 @@ struct hnm_renderer {
     float tmax_slack = 0.0f;
     int trace_blocks_per_sm = HNM_TRACE_MIN_BLOCKS;  // persistent CTAs per SM = what the register budget allows
     cudaEvent_t marks[16] = {};
+    std::function<void()> prefetch_hook;  // set by run_batch while a batch is being enqueued
     // multi-GPU gather target (hnm_group_* on device 0 of the group, hnm_dist_* on every rank): the shards of all ranks,
     // and the full image in row order
     double* gathered = nullptr;
@@ -227,7 +230,7 @@ void launch_nee_resolve(hnm_renderer* r, int bounce) {
 // k_trace over one or two ray lists; k_confirm for the FIRST list if `confirm_first` (a shadow-ray list is confirmed by
 // its consumer, k_nee_resolve)
 void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const TraceJob* j1, uint32_t* work, int stat_segments,
-                  bool confirm_first = true) {
+                  bool confirm_first = true, bool prefetch_behind_trace = false) {
     TraceArgs A;
     memset(&A, 0, sizeof(A));
     A.job[0] = *j0;
@@ -238,6 +241,7 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     A.stat_segments = stat_segments;
     A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
     A.tmax_slack = r->tmax_slack;
+    A.dbg = r->P.dbg;
     A.cand = r->cand;
     const int grid = r->sm_count * r->trace_blocks_per_sm;
     const int cgrid = r->sm_count * 8;
@@ -250,6 +254,7 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
         if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, C); });
     } else {
         launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
+        if (prefetch_behind_trace && r->prefetch_hook) r->prefetch_hook();
         if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, C); });
     }
 }
@@ -300,6 +305,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             return 0;
         };
         const bool want_prefetch = overlap && next_batch > 0;
+        int hook_rc = 0;
+        r->prefetch_hook = [&] { hook_rc = prefetch_next(); };
         if (want_prefetch && r->rng_start_bounce <= 0) { int rc = prefetch_next(); if (rc) return rc; }
         bind_gen_set(P, g);
         launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
@@ -307,17 +314,20 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             if (b == 1) select_first_bounce(r, g);
             else select_buffers(r, b & 1);  // bounce 2 reads queue 0 (written by bounce 1), bounce 3 queue 1, ...
             TraceJob cam = camera_job(P, b, true);
+            // HNM_RNG_MIDTRACE: the generation kernel is enqueued right BEHIND this bounce's trace launch with no dependency
+            // on it, so that its CTAs are placed while the trace CTAs are already resident (issue arbitration)
+            const bool mid = want_prefetch && r->rng_midtrace && b == r->rng_start_bounce;
             if (b > 1) {
                 TraceJob sh = shadow_job(P, b - 1);
-                launch_trace(r, trace_name(r, b), &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
+                launch_trace(r, trace_name(r, b), &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS, true, mid);
                 launch_nee_resolve(r, b - 1);
             } else {
-                launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS);
+                launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS, true, mid);
             }
             launch_timed(r, "shade_miss", [&] { k_shade_miss<<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_delta", [&] { k_shade_surf<false><<<grid, 256, 0, st>>>(P, b); });
             launch_timed(r, "shade_nee", [&] { k_shade_surf<true><<<grid, 256, 0, st>>>(P, b); });
-            if (want_prefetch && b == r->rng_start_bounce) {
+            if (want_prefetch && !r->rng_midtrace && b == r->rng_start_bounce) {
                 // the generation of the next batch starts here: the thin late bounces leave the SMs under-used
                 HNM_CUDA(cudaEventRecord(r->rng_gate, st));
                 HNM_CUDA(cudaStreamWaitEvent(r->rng_stream, r->rng_gate, 0));
@@ -329,6 +339,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
         launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1, false);
         launch_nee_resolve(r, last);
         launch_timed(r, "accumulate", [&] { k_accumulate<<<grid, 256, 0, st>>>(P); });
+        r->prefetch_hook = nullptr;
+        if (hook_rc) return hook_rc;
         HNM_CUDA(cudaEventRecord(g.released, st));
         g.released_recorded = true;
     } else {
@@ -483,6 +495,8 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_RNG_TAIL_K")) { int k = atoi(e); if (k >= 2 && k <= RNG_TAIL) P.tail_k = k & ~1; }
     if (const char* e = getenv("HNM_TRACE_STATS")) r->trace_stats = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_NAMES")) r->per_bounce_names = atoi(e) != 0;
+    if (const char* e = getenv("HNM_WID_STATS")) r->wid_stats = atoi(e) != 0;
+    if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
@@ -565,6 +579,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         A.take(&P.counters, (size_t)NUM_COUNTERS);
         A.take(&P.stats, (size_t)S_COUNT);
         A.take(&P.accum, accum_n);
+        if (r->wid_stats) A.take(&P.dbg, (size_t)8);
     };
     {
         Arena measure;
@@ -587,11 +602,13 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     bind_gen_set(P, r->gen[0]);
     ce = cudaMemsetAsync(P.accum, 0, accum_n * sizeof(double), r->stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(P.stats, 0, S_COUNT * sizeof(unsigned long long), r->stream);
+    if (ce == cudaSuccess && P.dbg) ce = cudaMemsetAsync(P.dbg, 0, 8 * sizeof(unsigned long long), r->stream);
     if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
         ce = cudaFuncSetAttribute(k_isaac_raygen, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_PATHS * 256 * (int)sizeof(uint64_t));
     if (const char* e = getenv("HNM_CARVEOUT")) {
         // experiment: the shared-memory carve-out the kernels that co-reside with k_isaac_raygen ask for
         int c = atoi(e);
+        cudaFuncSetAttribute(k_confirm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_shade_miss, cudaFuncAttributePreferredSharedMemoryCarveout, c);
@@ -640,6 +657,7 @@ int hnm_clear(hnm_renderer* r) {
     HNM_CUDA(cudaSetDevice(r->scene->device));
     HNM_CUDA(cudaMemsetAsync(r->P.accum, 0, (size_t)r->padded_rows * r->P.W * 3 * sizeof(double), r->stream));
     HNM_CUDA(cudaMemsetAsync(r->P.stats, 0, S_COUNT * sizeof(unsigned long long), r->stream));
+    if (r->P.dbg) HNM_CUDA(cudaMemsetAsync(r->P.dbg, 0, 8 * sizeof(unsigned long long), r->stream));
     r->launches = 0;
     return 0;
 }
@@ -731,7 +749,18 @@ int hnm_get_counters(hnm_renderer* r, hnm_counters* out) {
     HNM_CUDA(cudaStreamSynchronize(r->stream));
     out->paths = s[S_PATHS]; out->segments = s[S_SEGMENTS]; out->shadow_rays = s[S_SHADOW];
     out->rng_fallbacks = s[S_RNG_FALLBACK]; out->kernel_launches = r->launches;
-    out->node_visits = s[S_NODES]; out->prim_tests = s[S_PRIMS];
+    out->node_visits = s[S_NODES]; out->prim_tests = s[S_PRIMS]; out->cand_overflows = s[S_OVERFLOW];
+    return 0;
+}
+int hnm_debug_warp_slots(hnm_renderer* r, uint64_t* masks, uint32_t n) {
+    if (!r || !masks) return set_error(HNM_ERR_INVALID, "null argument");
+    for (uint32_t k = 0; k < n; k++) masks[k] = 0;
+    if (!r->P.dbg) return 0;
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    unsigned long long m[8];
+    HNM_CUDA(cudaMemcpyAsync(m, r->P.dbg, sizeof(m), cudaMemcpyDeviceToHost, r->stream));
+    HNM_CUDA(cudaStreamSynchronize(r->stream));
+    for (uint32_t k = 0; k < n && k < 8; k++) masks[k] = m[k];
     return 0;
 }
 int hnm_set_profiling(hnm_renderer* r, int enabled) {
@@ -888,6 +917,7 @@ int hnm_group_get_counters(hnm_group* g, hnm_counters* out) {
         if (rc) return rc;
         out->paths += c.paths; out->segments += c.segments; out->shadow_rays += c.shadow_rays; out->rng_fallbacks += c.rng_fallbacks;
         out->kernel_launches += c.kernel_launches; out->node_visits += c.node_visits; out->prim_tests += c.prim_tests;
+        out->cand_overflows += c.cand_overflows;
     }
     return 0;
 }

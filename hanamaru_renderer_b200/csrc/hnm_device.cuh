@@ -167,14 +167,21 @@ struct Hit {
     uint32_t id;    // triangle index (leaf order) or element id
 };
 
+// f64::min / f64::max of the reference's toolchain (Rust 1.20 .. 1.36 libcore: min = if other.is_nan() || self < other
+// { self } else { other }, max = if self.is_nan() || self < other { other } else { self }): NaN-ignoring like fmin / fmax,
+// but for operands that compare equal (+0.0 vs -0.0) min keeps the SECOND and max the FIRST operand, where the hardware
+// min / max order -0.0 below +0.0.  Only the slab test's sign-of-tmax check can see the difference.
+HNM_D double rs_min(double a, double b) { return (b != b || a < b) ? a : b; }
+HNM_D double rs_max(double a, double b) { return (a != a || a < b) ? b : a; }
+
 // ---------------------------------------------------------------- the reference's box chain
 // src/bvh.rs:20-39 on a stored box with the ray's reciprocal direction; also returns tmax
 HNM_D bool ref_box_hit(const double* __restrict__ b, D3 o, double ix, double iy, double iz, double& tmax) {
     const double t1 = (__ldg(b + 0) - o.x) * ix, t2 = (__ldg(b + 3) - o.x) * ix;
     const double t3 = (__ldg(b + 1) - o.y) * iy, t4 = (__ldg(b + 4) - o.y) * iy;
     const double t5 = (__ldg(b + 2) - o.z) * iz, t6 = (__ldg(b + 5) - o.z) * iz;
-    const double tmin = fmax(fmax(fmin(t1, t2), fmin(t3, t4)), fmin(t5, t6));  // f64::min / max ignore a NaN operand, like fmin / fmax
-    tmax = fmin(fmin(fmax(t1, t2), fmax(t3, t4)), fmax(t5, t6));
+    const double tmin = rs_max(rs_max(rs_min(t1, t2), rs_min(t3, t4)), rs_min(t5, t6));
+    tmax = rs_min(rs_min(rs_max(t1, t2), rs_max(t3, t4)), rs_max(t5, t6));
     return tmin <= tmax && !(__double2hiint(tmax) < 0);
 }
 HNM_D bool ref_chain_full(const RefNode* __restrict__ nodes, uint32_t node, D3 o, double ix, double iy, double iz) {
@@ -267,8 +274,8 @@ HNM_D bool aabb_intersect_ray(double mnx, double mny, double mnz, double mxx, do
     double t4 = (mxy - o.y) * iy;
     double t5 = (mnz - o.z) * iz;
     double t6 = (mxz - o.z) * iz;
-    double tmin = fmax(fmax(fmin(t1, t2), fmin(t3, t4)), fmin(t5, t6));
-    double tmax = fmin(fmin(fmax(t1, t2), fmax(t3, t4)), fmax(t5, t6));
+    double tmin = rs_max(rs_max(rs_min(t1, t2), rs_min(t3, t4)), rs_min(t5, t6));
+    double tmax = rs_min(rs_min(rs_max(t1, t2), rs_max(t3, t4)), rs_max(t5, t6));
     bool hit = tmin <= tmax && !signbit_(tmax);
     *distance = !signbit_(tmin) ? tmin : tmax;
     return hit;

@@ -79,6 +79,7 @@ struct TraceArgs {
     int stat_segments;              // stats index that receives job[0]'s ray count, or -1
     int stat_nodes, stat_prims;
     float tmax_slack;               // half-width of the window around tmax[] inside which the exact closest hit matters
+    unsigned long long* dbg;        // diagnostics: see RParams::dbg
 };
 
 HNM_D float l1(float x, float y, float z) { return fabsf(x) + fabsf(y) + fabsf(z); }
@@ -212,6 +213,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, HNM_TRACE_MIN_BLOCKS) k_trace(D
     const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
     const uint32_t ntot = n0 + n1;
     const float WLO = 1.0f - 4.76837158203125e-07f, WUP = 1.0f + 4.76837158203125e-07f;  // 1 -+ 2^-21, see hnm_device.cuh: trace()
+    if (A.dbg && lane == 0) {
+        unsigned w;
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(w));
+        atomicOr(&A.dbg[1], 1ull << (w & 63u));
+    }
 
     int32_t stack[HNM_STACK];
     int sp = 0;
@@ -488,6 +494,7 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
             // loads (header -> entries -> triangle) and latency is all it costs (ncu, round 1: 15 long-scoreboard
             // stall cycles per issued instruction)
             const uint32_t n = __ldcs(A.cand.n + slot);
+            if (STATS && n == CAND_OVERFLOW) atomicAdd(&A.stats[6], 1ull);  // S_OVERFLOW
             const float ub = __ldcs(A.cand.ub + slot);
             const uint32_t cid0 = __ldcs(A.cand.id + slot);   // entry 0 (unspecified if n == 0, always readable)
             const float lo0 = __ldcs(A.cand.lo + slot);

@@ -200,13 +200,32 @@ std::shared_ptr<ObjGeometry> AssetStore::obj(const std::string& path) const {
 std::shared_ptr<Image> AssetStore::image(const std::string& path) const {
     auto it = images_.find(path);
     if (it != images_.end()) return it->second;
-    throw std::runtime_error("image asset not found (decode it on the host and register it, or load a pack): " + path);
+    auto en = encoded_.find(path);
+    if (en != encoded_.end()) {
+        auto img = std::make_shared<Image>();
+        std::string err;
+        if (!image_decode(en->second->data(), en->second->size(), *img, &err)) throw std::runtime_error(path + ": " + err);
+        images_[path] = img;
+        return img;
+    }
+    if (!root_.empty()) {
+        std::string bytes;
+        if (read_all(root_ + "/" + path, bytes)) {  // `image::open` (src/texture.rs:18)
+            auto img = std::make_shared<Image>();
+            std::string err;
+            if (!image_decode((const uint8_t*)bytes.data(), bytes.size(), *img, &err)) throw std::runtime_error(path + ": " + err);
+            images_[path] = img;
+            return img;
+        }
+    }
+    throw std::runtime_error("image asset not found (set a root directory, register it, or load a pack): " + path);
 }
 
 // pack layout (little endian), written by tools/make_asset_pack.py:
 //   "HNMPACK1" u32 count { u32 name_len, name, u32 kind(1 mesh | 2 image), u32 a, u32 b, u64 raw, u64 comp, zlib bytes }
 //   mesh : a = vertex count, b = face count; payload = f64 xyz[a] then u32 v0v1v2[b]
 //   image: a = width, b = height;           payload = RGBA8 rows, top row first
+//   kind 3 = image file bytes (PNG / JPEG) as shipped by the reference, decoded on first use (a = b = 0)
 bool AssetStore::load_pack(const std::string& path, std::string* err) {
     std::string buf;
     if (!read_all(path, buf)) { if (err) *err = "cannot read " + path; return false; }
@@ -250,6 +269,9 @@ bool AssetStore::load_pack(const std::string& path, std::string* err) {
                 img->width = a; img->height = b;
                 img->rgba = std::move(data);
                 images_[name] = img;
+            } else if (kind == 3) {
+                // an image FILE as the reference ships it (PNG / JPEG bytes): decoded by image_decode on first use
+                encoded_[name] = std::make_shared<std::vector<uint8_t>>(std::move(data));
             } else {
                 throw std::runtime_error("unknown pack entry kind");
             }
@@ -1079,8 +1101,15 @@ uint32_t Renderer::render(const BvhScene& scene, const hnm_camera& camera, Image
     }
     uint32_t sampling = 0;
     const uint32_t limit = max_sampling();
+    // passes per call: the reference reports after EVERY pass (src/renderer.rs:41); a device call per pass would leave the
+    // GPU under-filled at small images (one 480x270 pass is 0.5 M paths; the wavefront wants 16 M in flight) and pay a host
+    // synchronisation each time.  `auto` asks for the number of passes that fills the device and lets the renderer shrink it
+    // as its time limit approaches (PathTracingRenderer::next_call_passes), so that `-t` still ends on time.
+    const uint64_t per_pass = (uint64_t)imgbuf.width * imgbuf.height * 4;
+    const uint32_t fill = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, ((16ull << 20) + per_pass - 1) / per_pass));
     while (sampling < limit) {
-        uint32_t n = passes_per_call ? std::min(passes_per_call, limit - sampling) : 1u;
+        uint32_t want = passes_per_call ? passes_per_call : next_call_passes(sampling, fill);
+        uint32_t n = std::max(1u, std::min(want, limit - sampling));
         if (api->render_passes(r_, sampling + 1, n) != 0 || api->synchronize(r_) != 0) { error = api->last_error(); break; }
         sampling += n;
         if (report_progress(sampling, imgbuf)) break;
@@ -1093,6 +1122,15 @@ uint32_t Renderer::render(const BvhScene& scene, const hnm_camera& camera, Image
 void Renderer::update_imgbuf(uint32_t sampling, ImageBuffer& imgbuf) {
     const CoreApi* api = core_api(nullptr);
     if (api && r_ && api->resolve(r_, nullptr, sampling, imgbuf.rgb.data()) != 0) error = api->last_error();
+}
+// src/renderer.rs:92-98: update_imgbuf, then `image::ImageRgb8(imgbuf.clone()).save(path)` with path = "{:>03}.png"
+void Renderer::save_progress_image(uint32_t counter, uint32_t sampling, ImageBuffer& imgbuf) {
+    update_imgbuf(sampling, imgbuf);
+    if (save_dir.empty() || !error.empty()) return;
+    char name[32];
+    snprintf(name, sizeof(name), "%03u.png", counter);
+    std::string err;
+    if (!save_png(save_dir + "/" + name, imgbuf.rgb.data(), imgbuf.width, imgbuf.height, &err)) error = err;
 }
 bool DebugRenderer::report_progress(uint32_t sampling, ImageBuffer& imgbuf) {  // src/renderer.rs:141-145
     update_imgbuf(sampling, imgbuf);
@@ -1110,17 +1148,51 @@ bool PathTracingRenderer::report_progress(uint32_t sampling, ImageBuffer& imgbuf
     const double from_last = now - last_report_progress_;
     if (verbose)
         fprintf(stderr, "rendering: %ux4 sampled (last %.3f sec). total: %.3f sec (%.2f %%).\n", sampling, from_last, used, used / time_limit_sec_ * 100.0);
-    if (used + from_last * 1.1 > time_limit_sec_ || sampling >= max_sampling()) {
-        update_imgbuf(sampling, imgbuf);
+    if (last_call_passes_ > 0) sec_per_pass_ = from_last / last_call_passes_;
+    // `offset = from_last_sampling_sec * 1.1` (src/renderer.rs:218): the prediction is for the NEXT call.  With a fixed
+    // passes_per_call that is a call like the last one; in auto mode the next call is sized to fit (plan_next), so the
+    // loop stops exactly when not even one more pass fits -- the reference's rule at one pass per call.
+    const double predicted = (last_call_passes_ ? sec_per_pass_ * plan_next(sampling, now) : from_last) * 1.1;
+    if (used + predicted > time_limit_sec_ || sampling >= max_sampling()) {
+        save_progress_image(report_image_counter_, sampling, imgbuf);
         return true;
     }
     if (now - last_report_image_ >= report_interval_sec_) {
-        update_imgbuf(sampling, imgbuf);
+        save_progress_image(report_image_counter_, sampling, imgbuf);
         report_image_counter_ += 1;
         last_report_image_ = now;
     }
-    last_report_progress_ = now;
+    last_report_progress_ = now_sec();
     return false;
+}
+// how many passes the next device call should run: the filling batch, shrunk so that (passes x the measured time per
+// pass x 1.1) still fits before the time limit and so that the next progress image is not overshot by a whole batch
+uint32_t PathTracingRenderer::plan_next(uint32_t sampling, double now) const {
+    if (!(sec_per_pass_ > 0.0)) return 1;  // the first call measures one pass
+    uint32_t n = std::max(1u, fill_);
+    const double left = time_limit_sec_ - (now - begin_);
+    const double fit = left / (sec_per_pass_ * 1.1);
+    if (fit < (double)n) n = fit >= 1.0 ? (uint32_t)fit : 1u;
+    const double to_report = report_interval_sec_ - (now - last_report_image_);
+    if (to_report > 0.0 && to_report / sec_per_pass_ < (double)n) n = std::max(1u, (uint32_t)std::ceil(to_report / sec_per_pass_));
+    const uint32_t remaining = max_sampling() > sampling ? max_sampling() - sampling : 1u;
+    return std::max(1u, std::min(n, remaining));
+}
+uint32_t PathTracingRenderer::next_call_passes(uint32_t sampling, uint32_t fill) {
+    fill_ = fill;
+    last_call_passes_ = plan_next(sampling, now_sec());
+    return last_call_passes_;
+}
+
+bool save_png(const std::string& path, const uint8_t* rgb, uint32_t width, uint32_t height, std::string* err) {
+    std::vector<uint8_t> bytes;
+    if (!png_encode_rgb8(rgb, width, height, bytes, err)) return false;
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) { if (err) *err = "cannot write " + path; return false; }
+    const bool ok = fwrite(bytes.data(), 1, bytes.size(), f) == bytes.size();
+    fclose(f);
+    if (!ok && err) *err = "short write to " + path;
+    return ok;
 }
 
 }  // namespace hanamaru

@@ -116,10 +116,17 @@ struct ObjGeometry {
     std::vector<uint32_t> faces;  // v0 v1 v2 triples, 0-based
 };
 
+// `image::open` / `DynamicImage::save` of the reference (src/texture.rs:18, src/renderer.rs:97, src/main.rs:1217):
+// hanamaru_image.cpp.  PNG (8/16-bit, all colour types, non-interlaced) and baseline JPEG decode; 8-bit RGB PNG encode.
+bool png_encode_rgb8(const uint8_t* rgb, uint32_t width, uint32_t height, std::vector<uint8_t>& out, std::string* err);
+bool png_decode(const uint8_t* data, size_t n, Image& out, std::string* err);
+bool jpeg_decode(const uint8_t* data, size_t n, Image& out, std::string* err);
+bool image_decode(const uint8_t* data, size_t n, Image& out, std::string* err);
+bool save_png(const std::string& path, const uint8_t* rgb, uint32_t width, uint32_t height, std::string* err);
+
 // Where OBJ files and decoded images come from: a directory laid out like the
-// reference checkout (OBJ only -- there is no PNG/JPEG decoder in this image's
-// C++ toolchain; images can be registered by the caller) and/or an asset pack
-// written by tools/make_asset_pack.py.
+// reference checkout (OBJ text and PNG / JPEG files, decoded here), images
+// registered by the caller, and/or an asset pack written by tools/make_asset_pack.py.
 class AssetStore {
   public:
     void set_root(const std::string& dir) { root_ = dir; }
@@ -131,6 +138,7 @@ class AssetStore {
   private:
     std::string root_;
     mutable std::map<std::string, std::shared_ptr<Image>> images_;
+    std::map<std::string, std::shared_ptr<std::vector<uint8_t>>> encoded_;  // image files from a pack, not decoded yet
     mutable std::map<std::string, std::shared_ptr<ObjGeometry>> objs_;
 };
 
@@ -335,10 +343,15 @@ class Renderer {
     // src/renderer.rs:62 -- true = stop
     virtual bool report_progress(uint32_t sampling, ImageBuffer& imgbuf) = 0;
     int device = 0;
-    uint32_t passes_per_call = 0;  // 0 = auto
+    uint32_t passes_per_call = 0;  // 0 = auto: as many passes per call as fill the device, fewer near the time limit
     std::string error;
+    // `save_progress_image` (src/renderer.rs:92-98): when non-empty, every image report_progress produces is also written
+    // as "<save_dir>/NNN.png" (NNN = the report counter), like the reference writes NNN.png into its cwd
+    std::string save_dir;
   protected:
     void update_imgbuf(uint32_t sampling, ImageBuffer& imgbuf);  // src/renderer.rs:64-90 via hnm_resolve
+    void save_progress_image(uint32_t counter, uint32_t sampling, ImageBuffer& imgbuf);  // src/renderer.rs:92-98
+    virtual uint32_t next_call_passes(uint32_t sampling, uint32_t fill) { (void)sampling; return fill; }
     hnm_renderer* r_ = nullptr;
 };
 
@@ -359,11 +372,16 @@ class PathTracingRenderer : public Renderer {  // src/renderer.rs:148-267
     int mode() const override { return HNM_MODE_PATHTRACING; }
     bool report_progress(uint32_t sampling, ImageBuffer& imgbuf) override;
     bool verbose = false;
+  protected:
+    uint32_t next_call_passes(uint32_t sampling, uint32_t fill) override;
   private:
     uint32_t sampling_;
     double time_limit_sec_, report_interval_sec_;
     double begin_, last_report_progress_, last_report_image_;
     uint32_t report_image_counter_ = 0;
+    uint32_t plan_next(uint32_t sampling, double now) const;
+    uint32_t last_call_passes_ = 0, fill_ = 1;
+    double sec_per_pass_ = 0.0;
 };
 
 }  // namespace hanamaru

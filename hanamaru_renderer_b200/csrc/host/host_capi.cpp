@@ -149,6 +149,60 @@ int hnmh_render(void* scene_handle, int mode, uint32_t width, uint32_t height, u
     HNMH_CATCH(-1)
 }
 
+// `image::open` on bytes in memory: *width / *height always; rgba (width * height * 4 bytes) when non-null.  Two-call
+// protocol: first with rgba == NULL to learn the size.
+int hnmh_image_decode(const uint8_t* bytes, size_t n, uint32_t* width, uint32_t* height, uint8_t* rgba) {
+    if (!bytes || !width || !height) { g_err = "null argument"; return -1; }
+    HNMH_TRY
+    Image img;
+    std::string err;
+    if (!image_decode(bytes, n, img, &err)) { g_err = err; return -1; }
+    *width = img.width; *height = img.height;
+    if (rgba) memcpy(rgba, img.rgba.data(), img.rgba.size());
+    return 0;
+    HNMH_CATCH(-1)
+}
+// `DynamicImage::save(path)` for an 8-bit RGB buffer (src/main.rs:1217 result.png, src/renderer.rs:97 NNN.png)
+int hnmh_save_png(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height) {
+    if (!path || !rgb) { g_err = "null argument"; return -1; }
+    HNMH_TRY
+    std::string err;
+    if (!save_png(path, rgb, width, height, &err)) { g_err = err; return -1; }
+    return 0;
+    HNMH_CATCH(-1)
+}
+// hnmh_render + the reference's file outputs: progress / final images as "<out_dir>/NNN.png" (src/renderer.rs:92-98) and
+// the final image as "<out_dir>/result.png" (src/main.rs:1217)
+int hnmh_render_to_files(void* scene_handle, int mode, uint32_t width, uint32_t height, uint32_t sampling, double time_limit_sec,
+                         double report_interval_sec, uint32_t passes_per_call, int device, const char* out_dir, uint8_t* rgb8,
+                         uint32_t* passes_done) {
+    if (!scene_handle || !out_dir || !passes_done) { g_err = "null argument"; return -1; }
+    HNMH_TRY
+    SceneHandle* h = (SceneHandle*)scene_handle;
+    ImageBuffer img(width, height);
+    uint32_t done = 0;
+    std::string err;
+    if (mode == HNM_MODE_PATHTRACING) {
+        PathTracingRenderer r(sampling, time_limit_sec, report_interval_sec);
+        r.device = device;
+        r.passes_per_call = passes_per_call;
+        r.save_dir = out_dir;
+        done = r.render(*h->bvh_scene, h->camera, img);
+        err = r.error;
+    } else {
+        DebugRenderer r(mode);
+        r.device = device;
+        done = r.render(*h->bvh_scene, h->camera, img);
+        err = r.error;
+    }
+    if (!err.empty()) { g_err = err; return -1; }
+    if (!save_png(std::string(out_dir) + "/result.png", img.rgb.data(), width, height, &err)) { g_err = err; return -1; }
+    if (rgb8) memcpy(rgb8, img.rgb.data(), img.rgb.size());
+    *passes_done = done;
+    return 0;
+    HNMH_CATCH(-1)
+}
+
 // rand 0.4.3 StdRng as the scene builders use it: `count` u64 outputs (kind 0) or gen_range(low, high) f64 draws
 // (kind 1, written as doubles) after skipping `skip` outputs -- for the known-answer tests
 int hnmh_stdrng(const uint64_t* seed, uint32_t nseed, uint32_t skip, uint32_t count, int kind, double low, double high, void* out) {

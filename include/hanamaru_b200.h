@@ -197,6 +197,7 @@ typedef struct hnm_counters {
     uint64_t kernel_launches;
     uint64_t node_visits;  /* BVH nodes fetched / primitives tested; counted only when */
     uint64_t prim_tests;   /* the environment has HNM_TRACE_STATS=1 (instrumented kernel) */
+    uint64_t cand_overflows; /* rays whose candidate list overflowed or that were routed to the exact traversal (HNM_TRACE_STATS=1) */
 } hnm_counters;
 
 typedef struct hnm_scene hnm_scene;       /* opaque: device copy of a scene */
@@ -263,6 +264,9 @@ int hnm_get_counters(hnm_renderer* r, hnm_counters* out);
  * events on the renderer's stream); names are static strings. */
 int hnm_get_kernel_times(hnm_renderer* r, uint32_t max, const char** names, float* ms, uint32_t* launches, uint32_t* n);
 int hnm_set_profiling(hnm_renderer* r, int enabled);
+/* Diagnostics (environment HNM_WID_STATS=1, else all zero): bit w of masks[k] = a warp of kernel class k
+ * (0 generation, 1 trace, 2 shade) ran in hardware warp slot w of its SM. */
+int hnm_debug_warp_slots(hnm_renderer* r, uint64_t* masks, uint32_t n);
 /* Device-side stopwatch on the renderer's own stream (torch.cuda.Event only sees torch's stream):
  * hnm_mark records CUDA event `slot` (0..15); hnm_elapsed_ms synchronises on both and returns b - a. */
 int hnm_mark(hnm_renderer* r, uint32_t slot);

@@ -251,6 +251,15 @@ Intersection empty_intersection(const Ctx& c) {  // src/scene.rs:26-39
     return i;
 }
 
+// f64::min / f64::max as the reference's toolchain defined them (Rust 1.20 .. 1.36, libcore/num/f64.rs, restated from
+// memory -- std is not in the tree):  min = (if other.is_nan() || self < other { self } else { other }) * 1.0,
+// max = (if self.is_nan() || self < other { other } else { self }) * 1.0.  Both ignore a NaN operand like C's fmin / fmax;
+// they differ from glibc only for operands that compare equal, i.e. +0.0 against -0.0: min keeps the SECOND operand,
+// max the FIRST.  Observable only in the slab test below (`tmax.is_sign_positive()`), and only when the ray origin lies
+// exactly on box planes of two axes.  Parity UNPINNED at this step (no artefact of the reference exercises it).
+inline double rs_min(double a, double b) { return (b != b || a < b) ? a : b; }
+inline double rs_max(double a, double b) { return (a != a || a < b) ? b : a; }
+
 // ---------------------------------------------------------------- src/bvh.rs:20-39
 inline bool aabb_intersect_ray(const double* mn, const double* mx, const Ray& ray, double* distance) {
     V3 dir_inv = v3(1.0 / ray.direction.x, 1.0 / ray.direction.y, 1.0 / ray.direction.z);
@@ -260,8 +269,8 @@ inline bool aabb_intersect_ray(const double* mn, const double* mx, const Ray& ra
     double t4 = (mx[1] - ray.origin.y) * dir_inv.y;
     double t5 = (mn[2] - ray.origin.z) * dir_inv.z;
     double t6 = (mx[2] - ray.origin.z) * dir_inv.z;
-    double tmin = std::fmax(std::fmax(std::fmin(t1, t2), std::fmin(t3, t4)), std::fmin(t5, t6));
-    double tmax = std::fmin(std::fmin(std::fmax(t1, t2), std::fmax(t3, t4)), std::fmax(t5, t6));
+    double tmin = rs_max(rs_max(rs_min(t1, t2), rs_min(t3, t4)), rs_min(t5, t6));  // (t1.min(t2).max(t3.min(t4))).max(t5.min(t6))
+    double tmax = rs_min(rs_min(rs_max(t1, t2), rs_max(t3, t4)), rs_max(t5, t6));
     bool hit = tmin <= tmax && !std::signbit(tmax);
     *distance = !std::signbit(tmin) ? tmin : tmax;
     return hit;

@@ -48,6 +48,27 @@ IMAGES = [
 ] + ["textures/cube/Powerlines/%s.jpg" % f for f in ("posx", "negx", "posy", "negy", "posz", "negz")]
 
 
+# Cube maps of the scenes that do not use Powerlines, shipped as the reference's own JPEG FILES (12 MB instead of 200 MB of
+# texels) in a second pack, assets/hanamaru_cubemaps.hnmpack; the C++ host decodes them (hanamaru_image.cpp).
+CUBEMAP_FILES = ["textures/cube/%s/%s.jpg" % (d, f) for d in ("LancellottiChapel", "Ryfjallet")
+                 for f in ("posx", "negx", "posy", "negy", "posz", "negz")]
+
+
+def write_pack(out, entries):
+    with open(out, "wb") as f:
+        f.write(b"HNMPACK1")
+        f.write(struct.pack("<I", len(entries)))
+        for name, kind, a, b, raw in entries:
+            comp = zlib.compress(raw, 9 if kind != 3 else 1)
+            nb = name.encode()
+            f.write(struct.pack("<I", len(nb)))
+            f.write(nb)
+            f.write(struct.pack("<IIIQQ", kind, a, b, len(raw), len(comp)))
+            f.write(comp)
+            print("%-55s kind=%d %8d x %-8d raw=%10d comp=%9d" % (name, kind, a, b, len(raw), len(comp)))
+    print("wrote", out, os.path.getsize(out), "bytes")
+
+
 def decode_rgba(path):
     """RGBA8, row 0 = top: DynamicImage::get_pixel semantics (Luma -> l,l,l,255; RGB -> r,g,b,255)."""
     im = Image.open(path)
@@ -78,18 +99,9 @@ def main():
         px = decode_rgba(os.path.join(ref, name))
         entries.append((name, 2, px.shape[1], px.shape[0], px.tobytes()))
 
-    with open(out, "wb") as f:
-        f.write(b"HNMPACK1")
-        f.write(struct.pack("<I", len(entries)))
-        for name, kind, a, b, raw in entries:
-            comp = zlib.compress(raw, 9)
-            nb = name.encode()
-            f.write(struct.pack("<I", len(nb)))
-            f.write(nb)
-            f.write(struct.pack("<IIIQQ", kind, a, b, len(raw), len(comp)))
-            f.write(comp)
-            print("%-55s kind=%d %8d x %-8d raw=%10d comp=%9d" % (name, kind, a, b, len(raw), len(comp)))
-    print("wrote", out, os.path.getsize(out), "bytes")
+    write_pack(out, entries)
+    cube = [(name, 3, 0, 0, open(os.path.join(ref, name), "rb").read()) for name in CUBEMAP_FILES]
+    write_pack(os.path.join(os.path.dirname(out), "hanamaru_cubemaps.hnmpack"), cube)
 
 
 if __name__ == "__main__":
