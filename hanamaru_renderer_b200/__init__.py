@@ -322,6 +322,11 @@ class RenderContext:
         _check(_ffi.core().hnm_debug_warp_slots(self._h, m, 4))
         return [int(x) for x in m]
 
+    def queue_counters(self, bounces=12):
+        m = (C.c_uint32 * (16 * bounces))()
+        _check(_ffi.core().hnm_debug_read_counters(self._h, m, 16 * bounces))
+        return np.array(m, dtype=np.uint32).reshape(bounces, 16)
+
     def set_profiling(self, on):
         _check(_ffi.core().hnm_set_profiling(self._h, int(on)))
 

@@ -135,6 +135,7 @@ CORE_SYMBOLS = {
     "hnm_get_kernel_times": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hnm_set_profiling": (C.c_int, [_P, C.c_int]),
     "hnm_debug_warp_slots": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint32]),
+    "hnm_debug_read_counters": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "hnm_mark": (C.c_int, [_P, C.c_uint32]),
     "hnm_elapsed_ms": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
     "hnm_intersect_batch": (C.c_int, [_P, _P, C.c_uint32, _P]),

@@ -59,6 +59,7 @@ struct hnm_renderer {
     uint8_t* rgb8 = nullptr;
     uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
     bool profiling = false, trace_stats = false, per_bounce_names = false, wid_stats = false;
+    bool profile_overlap = false;
     bool rng_midtrace = false;     // HNM_RNG_MIDTRACE=1: the prefetch is enqueued right behind a trace launch, without waiting for it
     uint64_t launches = 0;
     KernelTimer timer;
@@ -233,6 +234,7 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
                   bool confirm_first = true, bool prefetch_behind_trace = false) {
     TraceArgs A;
     memset(&A, 0, sizeof(A));
+    A.work_confirm = work + (C_W_CONFIRM - C_WORK);  // same bounce row of counters[]
     A.job[0] = *j0;
     A.njobs = 1;
     if (j1) { A.job[1] = *j1; A.njobs = 2; }
@@ -272,7 +274,9 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
     const int grid = r->sm_count * 4;
     const int last = (int)P.sc.bounce_limit - 1;
     if (P.mode == HNM_MODE_PATHTRACING) {
-        const bool overlap = r->overlap && !r->profiling && r->num_gen == 2;
+        // per-kernel timing normally serialises the two streams (clean numbers per kernel); HNM_PROFILE_OVERLAP=1 keeps the
+        // overlap on, so that the event pairs show how long each kernel takes WHILE the generation kernel is co-resident
+        const bool overlap = r->overlap && (!r->profiling || r->profile_overlap) && r->num_gen == 2;
         // ---- the generation set of this batch: prefetched, or generated now
         int s = -1;
         for (int k = 0; k < r->num_gen; k++)
@@ -497,6 +501,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_TRACE_NAMES")) r->per_bounce_names = atoi(e) != 0;
     if (const char* e = getenv("HNM_WID_STATS")) r->wid_stats = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
+    if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
@@ -763,6 +768,15 @@ int hnm_debug_warp_slots(hnm_renderer* r, uint64_t* masks, uint32_t n) {
     for (uint32_t k = 0; k < n && k < 8; k++) masks[k] = m[k];
     return 0;
 }
+// Diagnostics: the per-bounce queue counters of the LAST batch (row b = bounce b, 16 words: rays, miss, delta, nee, events,
+// shadow rays, then the work counters)
+int hnm_debug_read_counters(hnm_renderer* r, uint32_t* out, uint32_t n) {
+    if (!r || !out) return set_error(HNM_ERR_INVALID, "null argument");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    HNM_CUDA(cudaMemcpyAsync(out, r->P.counters, sizeof(uint32_t) * std::min<uint32_t>(n, NUM_COUNTERS), cudaMemcpyDeviceToHost, r->stream));
+    HNM_CUDA(cudaStreamSynchronize(r->stream));
+    return 0;
+}
 int hnm_set_profiling(hnm_renderer* r, int enabled) {
     if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
     r->timer.reset();
@@ -1009,6 +1023,7 @@ int hnm_intersect_batch(hnm_scene* scene, const hnm_ray* rays, uint32_t n, hnm_h
     A.job[0].count = cnt;
     A.njobs = 1;
     A.work = cnt + 1;
+    A.work_confirm = cnt + 2;
     A.stats = dstats;
     A.stat_segments = -1; A.stat_nodes = S_NODES; A.stat_prims = S_PRIMS;
     A.cand = cl;

@@ -396,7 +396,10 @@ HNM_D uchar4 texel_screen(const DImage& im, uint32_t x, uint32_t y) {  // src/te
 // One out-of-line copy per module: it is called from every shading kernel.  ptxas 12.9 (sm_100a, -O3) has produced a
 // wrong THIRD component of this function's result in some kernels for some shapes of this code (PTX correct, SASS
 // wrong); tests/test_gpu_parity.py pins every kernel that calls it bit-for-bit.
-__device__ __noinline__ void sample_bilinear_to(const double* __restrict__ unorm8, double gamma, DImage im, double u, double v,
+#ifndef HNM_BILINEAR_ATTR
+#define HNM_BILINEAR_ATTR __device__ __noinline__
+#endif
+HNM_BILINEAR_ATTR void sample_bilinear_to(const double* __restrict__ unorm8, double gamma, DImage im, double u, double v,
                                                 double* out) {  // src/texture.rs:29-49
     const double x = u * (double)im.width;
     const double y = v * (double)im.height;

@@ -54,7 +54,9 @@ __device__ __forceinline__ int isaac_slot() {
 constexpr int MAX_BOUNCE = 64;
 
 // counters[]: per bounce b (1-origin) eight slots
-enum { C_RAY = 0, C_MISS = 1, C_DELTA = 2, C_NEE = 3, C_EVENTS = 4, C_SHADOW = 5, C_WORK = 6, C_STRIDE = 8 };
+enum { C_RAY = 0, C_MISS = 1, C_DELTA = 2, C_NEE = 3, C_EVENTS = 4, C_SHADOW = 5, C_WORK = 6,
+       // dynamic work counters of the kernels after k_trace (zero at batch start): see fetch_warp / fetch_cta
+       C_W_CONFIRM = 7, C_W_MISS = 8, C_W_DELTA = 9, C_W_NEE = 10, C_W_NEER = 11, C_STRIDE = 16 };
 constexpr int NUM_COUNTERS = (MAX_BOUNCE + 2) * C_STRIDE + 8;
 // stats[] (u64)
 enum { S_PATHS = 0, S_SEGMENTS = 1, S_SHADOW = 2, S_RNG_FALLBACK = 3, S_NODES = 4, S_PRIMS = 5, S_OVERFLOW = 6, S_COUNT = 8 };
@@ -396,6 +398,40 @@ __global__ void k_raygen_debug(RParams P) {
     }
 }
 
+// Dynamic work distribution.  A static grid-stride loop gives every CTA of the grid the same share of the items; when
+// fewer CTAs are resident than the grid has (the generation kernel of the NEXT batch holds an SM's shared memory and
+// 8-9 K registers while these kernels run), the shares of the CTAs that did not fit run as a second, nearly empty wave.
+// Fetching 32 (warp) or blockDim (CTA) consecutive items at a time from a counter lets whatever is resident drain the
+// queue evenly.  Which warp handles which item never changes a result: every path's arithmetic is its own.
+#ifndef HNM_DYN_MISS
+#define HNM_DYN_MISS 1
+#endif
+#ifndef HNM_DYN_SURF
+// k_shade_surf keeps its static grid-stride loop.  With dynamic fetching (either formulation below) the 64-register build
+// of this kernel -- the one that spills to local memory -- gave wrong, run-to-run varying results on the one scene whose
+// floor samples two image textures per hit (rtcamp5_pl), while compute-sanitizer racecheck / synccheck / initcheck were
+// clean and the same source compiled for 80 or 128 registers was bit-exact again (the ptxas hazard).
+// Measured gain of the dynamic variant where it was correct: 0.5 %.
+#define HNM_DYN_SURF 0
+#endif
+#ifndef HNM_DYN_NEER
+#define HNM_DYN_NEER 1
+#endif
+#ifndef HNM_DYN_CONFIRM
+#define HNM_DYN_CONFIRM 1
+#endif
+HNM_D uint32_t fetch_warp(uint32_t* counter) {
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(counter, 32u);
+    return __shfl_sync(0xFFFFFFFFu, base, 0);
+}
+HNM_D uint32_t fetch_cta(uint32_t* counter) {  // all threads of the CTA must call; the caller must place a barrier before the next call
+    __shared__ uint32_t s_chunk;
+    if (threadIdx.x == 0) s_chunk = atomicAdd(counter, blockDim.x);
+    __syncthreads();
+    return s_chunk;
+}
+
 // slot in a compacted queue for every lane with `pred`; one atomic per warp
 HNM_D uint32_t queue_alloc(bool pred, uint32_t* counter) {
     unsigned mask = __ballot_sync(0xFFFFFFFFu, pred);
@@ -460,7 +496,16 @@ HNM_D Rand2 bounce_random(const RParams& P, uint32_t pid, int bounce) {
 #endif
 __global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams P, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_MISS];
+    uint32_t* const work = &P.counters[bounce * C_STRIDE + C_W_MISS];
+#if HNM_DYN_MISS
+    for (;;) {
+        const uint32_t base = fetch_warp(work);
+        if (base >= n) break;
+        const uint32_t i = base + (threadIdx.x & 31);
+        if (i >= n) continue;
+#else
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#endif
         uint32_t q = P.q_miss[i];
         uint32_t pid = P.pin[q];
         D3 d = load_ray_d(P, q);
@@ -490,9 +535,23 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
     const bool last_bounce = (uint32_t)bounce + 1 >= P.sc.bounce_limit;
     const uint32_t nl = P.sc.num_emissions;
     uint32_t shadow_rays = 0;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t n_round = (n + 255u) & ~255u;  // CTA-uniform trip count (blockDim.x == 256): barriers inside
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+    uint32_t* const work = &P.counters[bounce * C_STRIDE + (NEE ? C_W_NEE : C_W_DELTA)];
+#if HNM_DYN_SURF == 2
+    for (;;) {
+        // every warp fetches its own 32 items; the CTA leaves the loop together (barriers inside the body)
+        const uint32_t wbase = fetch_warp(work);
+        if (!__syncthreads_or(wbase < n ? 1 : 0)) break;
+        const uint32_t i = wbase < n ? wbase + (threadIdx.x & 31) : 0xFFFFFFFFu;
+#elif HNM_DYN_SURF
+    for (;;) {
+        __syncthreads();  // the previous iteration's readers of the chunk base are done
+        const uint32_t chunk = fetch_cta(work);  // CTA-uniform: barriers inside the body
+        if (chunk >= n) break;
+        const uint32_t i = chunk + threadIdx.x;
+#else
+    const uint32_t n_round = (n + 255u) & ~255u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+#endif
         bool alive = false, event = false;
         D3 no = splat(0.0), nd = splat(0.0), nthr = splat(0.0), thr = splat(0.0), view = splat(0.0);
         SurfacePoint sp;
@@ -588,7 +647,16 @@ __global__ void __launch_bounds__(256, HNM_NEER_MIN_BLOCKS) k_nee_resolve(RParam
     const uint32_t nl = P.sc.num_emissions;
     const DScene& sc = P.sc;
     uint32_t n_prims = 0;
+    uint32_t* const work = &P.counters[bounce * C_STRIDE + C_W_NEER];
+#if HNM_DYN_NEER
+    for (;;) {
+        const uint32_t base = fetch_warp(work);
+        if (base >= n) break;
+        const uint32_t ev = base + (threadIdx.x & 31);
+        if (ev >= n) continue;
+#else
     for (uint32_t ev = blockIdx.x * blockDim.x + threadIdx.x; ev < n; ev += gridDim.x * blockDim.x) {
+#endif
         D3 accumulation = splat(0.0);
         for (uint32_t k = 0; k < nl; k++) {
             size_t s = (size_t)ev * nl + k;

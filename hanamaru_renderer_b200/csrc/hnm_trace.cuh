@@ -74,6 +74,7 @@ struct TraceArgs {
     TraceJob job[2];
     CandLists cand;
     uint32_t* work;                 // global fetch counter, zero at launch
+    uint32_t* work_confirm;         // the same for k_confirm
     unsigned long long* stats;      // S_* counters
     int njobs;
     int stat_segments;              // stats index that receives job[0]'s ray count, or -1
@@ -480,10 +481,23 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
     const uint32_t n0 = *A.job[0].count;
     const uint32_t n1 = A.njobs > 1 ? *A.job[1].count : 0u;
     const uint32_t ntot = n0 + n1;
-    const uint32_t n_round = (ntot + 31u) & ~31u;  // warp-uniform trip count: the queue pushes ballot
     uint32_t n_prims = 0;
     const bool classify = A.job[0].q_miss != nullptr;
+#ifndef HNM_DYN_CONFIRM
+#define HNM_DYN_CONFIRM 1
+#endif
+#if HNM_DYN_CONFIRM
+    for (;;) {
+        // 32 consecutive rays per fetch (dynamic: see fetch_warp in hnm_kernels.cuh); warp-uniform: the queue pushes ballot
+        uint32_t wbase = 0;
+        if (lane == 0) wbase = atomicAdd(A.work_confirm, 32u);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        if (wbase >= ntot) break;
+        const uint32_t idx = wbase + lane;
+#else
+    const uint32_t n_round = (ntot + 31u) & ~31u;
     for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_round; idx += gridDim.x * blockDim.x) {
+#endif
         int cls = -1;
         if (idx < ntot) {
             const bool j1 = idx >= n0;

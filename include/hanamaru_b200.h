@@ -267,6 +267,9 @@ int hnm_set_profiling(hnm_renderer* r, int enabled);
 /* Diagnostics (environment HNM_WID_STATS=1, else all zero): bit w of masks[k] = a warp of kernel class k
  * (0 generation, 1 trace, 2 shade) ran in hardware warp slot w of its SM. */
 int hnm_debug_warp_slots(hnm_renderer* r, uint64_t* masks, uint32_t n);
+/* Diagnostics: the queue counters of the last batch, 16 words per bounce (rays, misses, delta hits, NEE hits, NEE events,
+ * shadow rays, work counters). */
+int hnm_debug_read_counters(hnm_renderer* r, uint32_t* out, uint32_t n);
 /* Device-side stopwatch on the renderer's own stream (torch.cuda.Event only sees torch's stream):
  * hnm_mark records CUDA event `slot` (0..15); hnm_elapsed_ms synchronises on both and returns b - a. */
 int hnm_mark(hnm_renderer* r, uint32_t slot);

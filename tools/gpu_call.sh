@@ -40,6 +40,43 @@ for step in "$@"; do
       } > $OUT/ab_prio.log 2>&1; cat $OUT/ab_prio.log ;;
     golden_s) HNM_GOLDEN_REPORT=$OUT/golden.json timeout 900 python -m pytest tests/test_reference_golden.py tests/test_gpu_reference_chain.py -m gpu -q -s > $OUT/golden.log 2>&1; grep -v "^$" $OUT/golden.log | tail -30 ;;
     multi)   timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -rfs > $OUT/multi.log 2>&1; tail -15 $OUT/multi.log ;;
+    prio)    { for a in "7 1" "7 0" "4 1"; do echo "== competitor CTAs/SM, ilp: $a"; timeout 120 _variants/prio $a; done; } > $OUT/prio.log 2>&1; cat $OUT/prio.log ;;
+    edge)    timeout 900 python -m pytest tests/test_gpu_edge_cases.py -m gpu -q -s -rf > $OUT/edge.log 2>&1; grep -v "^$" $OUT/edge.log | tail -25 ;;
+    stats3)  { for sc in bvh_heavy rtcamp6; do HNM_TRACE_STATS=1 timeout 300 python tools/time_passes.py $sc 1920 1080 6; done; } > $OUT/stats3.log 2>&1; cat $OUT/stats3.log ;;
+    parity)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_edge_cases.py tests/test_gpu_multi.py -m gpu -q -x -rf > $OUT/parity.log 2>&1; tail -8 $OUT/parity.log ;;
+    corun)   { bash tools/ab.sh "HNM_X=0" "HNM_PROFILE_OVERLAP=1" "HNM_RNG_OVERLAP=0"; for sc in diamond; do HNM_PROFILE_OVERLAP=1 timeout 200 python tools/time_passes.py $sc 1920 1080 9 2>&1 | tail -3; done; } > $OUT/corun.log 2>&1; cat $OUT/corun.log ;;
+    bench2s) timeout 600 python bench.py --config 2 --steps 8 --no-e2e --no-cpu --no-traffic > $OUT/bench2s.json 2> $OUT/bench2s.err; python -c "
+import json,sys
+d=json.loads(open('$OUT/bench2s.json').read().strip().splitlines()[-1]); print('config2 value', d['value'], 'ms/pass', d['ms_per_step']/d['config']['passes_per_step'], {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items()})" ;;
+    bench4s) timeout 600 python bench.py --config 4 --steps 2 --no-e2e --no-cpu --no-traffic > $OUT/bench4s.json 2> $OUT/bench4s.err; python -c "
+import json,sys
+d=json.loads(open('$OUT/bench4s.json').read().strip().splitlines()[-1]); print('config4 value', d['value'], 'ms/pass', d['ms_per_step']/d['config']['passes_per_step'])" ;;
+    bench3s) timeout 600 python bench.py --config 3 --steps 4 --no-e2e --no-cpu --no-traffic > $OUT/bench3s.json 2> $OUT/bench3s.err; python -c "
+import json,sys
+d=json.loads(open('$OUT/bench3s.json').read().strip().splitlines()[-1]); print('config3 value', d['value'], 'ms/pass', d['ms_per_step']/d['config']['passes_per_step'], {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items()})" ;;
+    bisect)  { for lib in "" _variants/nodyn.so _variants/nomiss.so _variants/nosurf.so _variants/noneer.so _variants/noconf.so; do
+                 HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -2; done
+               HNM_RNG_OVERLAP=0 timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -2
+               timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 1 2>&1 | tail -2
+               timeout 200 python tools/diag_scene.py tbf3_pl 160 90 1 2 2>&1 | tail -2; } > $OUT/bisect.log 2>&1; cat $OUT/bisect.log ;;
+    race)    { timeout 600 compute-sanitizer --tool racecheck --racecheck-report all python tools/diag_scene.py rtcamp5_pl 64 36 1 1 2>&1 | grep -v "^$" | head -80;
+               timeout 600 compute-sanitizer --tool synccheck python tools/diag_scene.py rtcamp5_pl 64 36 1 1 2>&1 | grep -v "^$" | head -40; } > $OUT/race.log 2>&1; head -c 7000 $OUT/race.log ;;
+    bisect2) { for lib in _variants/surf2.so _variants/surf1nosort.so _variants/surf2nosort.so; do
+                 HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -2; done; } > $OUT/bisect2.log 2>&1; cat $OUT/bisect2.log ;;
+    bisect3) { export HNM_DIAG_QUEUES=1; for lib in _variants/nosurf.so ""; do
+                 HNM_CORE_LIB=$lib HNM_RNG_OVERLAP=0 timeout 200 python tools/diag_scene.py rtcamp5_pl 64 36 1 1 2>&1 | tail -4; done; } > $OUT/bisect3.log 2>&1; cat $OUT/bisect3.log ;;
+    bisect4) { for lib in _variants/dynO1.so _variants/dyninl.so _variants/dyn3blk.so; do
+                 HNM_CORE_LIB=$lib HNM_RNG_OVERLAP=0 timeout 200 python tools/diag_scene.py rtcamp5_pl 64 36 1 1 2>&1 | tail -2; done;
+               HNM_RNG_OVERLAP=0 timeout 300 compute-sanitizer --tool initcheck python tools/diag_scene.py rtcamp5_pl 64 36 1 1 2>&1 | grep -v "^$" | head -40; } > $OUT/bisect4.log 2>&1; head -c 5000 $OUT/bisect4.log ;;
+    abdyn)   { for lib in _variants/nodyn.so _variants/nosurf.so _variants/dynblk3.so _variants/dyn3blk.so; do
+                 echo "== $lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -1 | cut -c1-80
+                 HNM_CORE_LIB=$lib timeout 300 python bench.py --config 2 --steps 8 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config2', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3), {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items() if k in ('confirm','shade_miss','shade_delta','shade_nee','nee_resolve')})"
+                 HNM_CORE_LIB=$lib timeout 300 python bench.py --config 4 --steps 2 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config4', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"
+               done; } > $OUT/abdyn.log 2>&1; cat $OUT/abdyn.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
