@@ -327,6 +327,10 @@ class RenderContext:
         _check(_ffi.core().hnm_debug_read_counters(self._h, m, 16 * bounces))
         return np.array(m, dtype=np.uint32).reshape(bounces, 16)
 
+    def set_precision(self, precision):
+        """_ffi.PRECISION_EXACT (default, bit parity) or _ffi.PRECISION_FAST_MATH (opt-in, statistical parity)."""
+        _check(_ffi.core().hnm_set_precision(self._h, int(precision)))
+
     def set_profiling(self, on):
         _check(_ffi.core().hnm_set_profiling(self._h, int(on)))
 

@@ -134,6 +134,7 @@ CORE_SYMBOLS = {
     "hnm_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "hnm_get_kernel_times": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "hnm_set_profiling": (C.c_int, [_P, C.c_int]),
+    "hnm_set_precision": (C.c_int, [_P, C.c_int]),
     "hnm_debug_warp_slots": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_uint32]),
     "hnm_debug_read_counters": (C.c_int, [_P, C.POINTER(C.c_uint32), C.c_uint32]),
     "hnm_mark": (C.c_int, [_P, C.c_uint32]),
@@ -162,6 +163,7 @@ CORE_SYMBOLS = {
     "hnm_dist_read_accum": (C.c_int, [_P, _P]),
 }
 HNM_DIST_ID_BYTES = 128
+PRECISION_EXACT, PRECISION_FAST_MATH = 0, 1
 
 HOST_SYMBOLS = {
     "hnmh_last_error": (C.c_char_p, []),

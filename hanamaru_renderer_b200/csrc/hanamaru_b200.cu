@@ -60,6 +60,8 @@ struct hnm_renderer {
     uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
     bool profiling = false, trace_stats = false, per_bounce_names = false, wid_stats = false;
     bool profile_overlap = false;
+    bool confirm_tma = false;      // HNM_CONFIRM_TMA=1: the TMA-staged k_confirm (A/B)
+    bool fast_math = false;        // hnm_set_precision(HNM_PRECISION_FAST_MATH): opt-in, statistical parity only
     bool rng_midtrace = false;     // HNM_RNG_MIDTRACE=1: the prefetch is enqueued right behind a trace launch, without waiting for it
     uint64_t launches = 0;
     KernelTimer timer;
@@ -224,8 +226,9 @@ void launch_nee_resolve(hnm_renderer* r, int bounce) {
     RParams& P = r->P;
     cudaStream_t st = r->stream;
     CandLists cand = r->cand;
-    if (r->trace_stats) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<true><<<grid, 256, 0, st>>>(P, cand, bounce); });
-    else launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false><<<grid, 256, 0, st>>>(P, cand, bounce); });
+    if (r->trace_stats) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<true, false><<<grid, 256, 0, st>>>(P, cand, bounce); });
+    else if (r->fast_math) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, true><<<grid, 256, 0, st>>>(P, cand, bounce); });
+    else launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, false><<<grid, 256, 0, st>>>(P, cand, bounce); });
 }
 
 // k_trace over one or two ray lists; k_confirm for the FIRST list if `confirm_first` (a shadow-ray list is confirmed by
@@ -257,7 +260,8 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     } else {
         launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
         if (prefetch_behind_trace && r->prefetch_hook) r->prefetch_hook();
-        if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, C); });
+        if (confirm_first && r->confirm_tma) launch_timed(r, "confirm", [&] { k_confirm_tma<false><<<r->sm_count * HNM_CONFIRM_MIN_BLOCKS, 256, 0, st>>>(sc, C); });
+        else if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, C); });
     }
 }
 
@@ -328,9 +332,15 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             } else {
                 launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS, true, mid);
             }
-            launch_timed(r, "shade_miss", [&] { k_shade_miss<<<grid, 256, 0, st>>>(P, b); });
-            launch_timed(r, "shade_delta", [&] { k_shade_surf<false><<<grid, 256, 0, st>>>(P, b); });
-            launch_timed(r, "shade_nee", [&] { k_shade_surf<true><<<grid, 256, 0, st>>>(P, b); });
+            if (r->fast_math) {
+                launch_timed(r, "shade_miss", [&] { k_shade_miss<true><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, true><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, true><<<grid, 256, 0, st>>>(P, b); });
+            } else {
+                launch_timed(r, "shade_miss", [&] { k_shade_miss<false><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<grid, 256, 0, st>>>(P, b); });
+            }
             if (want_prefetch && !r->rng_midtrace && b == r->rng_start_bounce) {
                 // the generation of the next batch starts here: the thin late bounces leave the SMs under-used
                 HNM_CUDA(cudaEventRecord(r->rng_gate, st));
@@ -502,6 +512,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_WID_STATS")) r->wid_stats = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
+    if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
@@ -616,10 +627,10 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         cudaFuncSetAttribute(k_confirm<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-        cudaFuncSetAttribute(k_shade_miss, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-        cudaFuncSetAttribute(k_shade_surf<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-        cudaFuncSetAttribute(k_shade_surf<true>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
-        cudaFuncSetAttribute(k_nee_resolve<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_miss<false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_surf<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_shade_surf<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
+        cudaFuncSetAttribute(k_nee_resolve<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, c);
         cudaFuncSetAttribute(k_batch_begin, cudaFuncAttributePreferredSharedMemoryCarveout, c);
     }
@@ -775,6 +786,12 @@ int hnm_debug_read_counters(hnm_renderer* r, uint32_t* out, uint32_t n) {
     HNM_CUDA(cudaSetDevice(r->scene->device));
     HNM_CUDA(cudaMemcpyAsync(out, r->P.counters, sizeof(uint32_t) * std::min<uint32_t>(n, NUM_COUNTERS), cudaMemcpyDeviceToHost, r->stream));
     HNM_CUDA(cudaStreamSynchronize(r->stream));
+    return 0;
+}
+int hnm_set_precision(hnm_renderer* r, int precision) {
+    if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
+    if (precision != HNM_PRECISION_EXACT && precision != HNM_PRECISION_FAST_MATH) return set_error(HNM_ERR_INVALID, "bad precision");
+    r->fast_math = precision == HNM_PRECISION_FAST_MATH;
     return 0;
 }
 int hnm_set_profiling(hnm_renderer* r, int enabled) {

@@ -423,16 +423,50 @@ HNM_BILINEAR_ATTR void sample_bilinear_to(const double* __restrict__ unorm8, dou
         out[k] = dm::pow(g, gamma);  // gamma_to_linear
     }
 }
+// FAST (opt-in perf mode, hnm_set_precision): the texture path of the shading kernels in f32 -- bilinear blend, powf --
+// plus sincosf per BSDF sample and acosf for sphere uv, instead of the f64 blend and the deterministic double-double
+// library.  Results are then statistically, not bit-wise, equal to the reference's.  A function of its own: the exact one
+// above must keep the code shape the parity tests pinned.
+#ifndef HNM_FAST_POW
+#define HNM_FAST_POW 1
+#endif
+#ifndef HNM_FAST_ACOS
+#define HNM_FAST_ACOS 1
+#endif
+#ifndef HNM_FAST_SINCOS
+#define HNM_FAST_SINCOS 1
+#endif
+__device__ __noinline__ float3 sample_bilinear_fast(float gamma, DImage im, float u, float v) {
+    const float x = u * (float)im.width, y = v * (float)im.height;
+    const float x1 = floorf(x), y1 = floorf(y);
+    const uint32_t ix = (uint32_t)fmaxf(x1, 0.0f), iy = (uint32_t)fmaxf(y1, 0.0f);
+    const uchar4 t11 = texel_screen(im, ix, iy), t12 = texel_screen(im, ix, iy + 1u);
+    const uchar4 t21 = texel_screen(im, ix + 1u, iy), t22 = texel_screen(im, ix + 1u, iy + 1u);
+    const float bx = x - x1, by = y - y1, ax = 1.0f - bx, ay = 1.0f - by;
+    const float w11 = ax * ay * (1.0f / 255.0f), w21 = bx * ay * (1.0f / 255.0f), w12 = ax * by * (1.0f / 255.0f), w22 = bx * by * (1.0f / 255.0f);
+    float3 c;
+    c.x = powf(t11.x * w11 + t21.x * w21 + t12.x * w12 + t22.x * w22, gamma);
+    c.y = powf(t11.y * w11 + t21.y * w21 + t12.y * w12 + t22.y * w22, gamma);
+    c.z = powf(t11.z * w11 + t21.z * w21 + t12.z * w12 + t22.z * w22, gamma);
+    return c;
+}
+template <bool FAST = false>
 HNM_D D3 sample_bilinear(const double* unorm8, double gamma, DImage im, double u, double v) {
+    if (FAST && HNM_FAST_POW) {
+        const float3 c = sample_bilinear_fast((float)gamma, im, (float)u, (float)v);
+        return d3((double)c.x, (double)c.y, (double)c.z);
+    }
     double r[3];
     sample_bilinear_to(unorm8, gamma, im, u, v, r);
     return d3(r[0], r[1], r[2]);
 }
+template <bool FAST = false>
 HNM_D D3 texture_sample(const DScene& sc, const DTexture& t, double u, double v) {  // src/texture.rs:108-114
-    if (t.image >= 0) return sample_bilinear(sc.unorm8, sc.gamma, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
+    if (t.image >= 0) return sample_bilinear<FAST>(sc.unorm8, sc.gamma, sc.images[t.image], u, v) * d3(t.r, t.g, t.b);
     return d3(t.r, t.g, t.b);
 }
 // src/scene.rs:295-319
+template <bool FAST = false>
 HNM_D D3 skybox_sample(const DScene& sc, D3 direction) {
     double abs_x = fabs(direction.x), abs_y = fabs(direction.y), abs_z = fabs(direction.z);
     int face;
@@ -450,7 +484,7 @@ HNM_D D3 skybox_sample(const DScene& sc, D3 direction) {
     // sample_bilinear_0center (src/texture.rs:22-26)
     // the six faces live in device memory: a run-time index into a kernel-PARAMETER array makes nvcc 12.9 spill the
     // parameter struct to local memory, and the copy it generated in one kernel was wrong (blue intensity garbage)
-    D3 c = sample_bilinear(sc.unorm8, sc.gamma, sc.sky_faces[face], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
+    D3 c = sample_bilinear<FAST>(sc.unorm8, sc.gamma, sc.sky_faces[face], 0.5 * (u + 1.0), 0.5 * (v + 1.0));
     return d3(sc.sky_r, sc.sky_g, sc.sky_b) * c;
 }
 
@@ -466,6 +500,7 @@ struct SurfacePoint {
     int32_t element, face;
 };
 // recompute what the winning `intersect` call wrote into the Intersection (same formulas, same bits)
+template <bool FAST = false>
 HNM_D SurfacePoint surface_point(const DScene& sc, const Hit& h, D3 o, D3 dir, bool need_uv) {
     SurfacePoint s;
     s.position = o + dir * h.t;
@@ -480,9 +515,9 @@ HNM_D SurfacePoint surface_point(const DScene& sc, const Hit& h, D3 o, D3 dir, b
         s.element = (int32_t)h.id;
         s.normal = normalize(s.position - d3(e.ax, e.ay, e.az));  // src/scene.rs:67
         if (need_uv) {  // src/scene.rs:69-73 (only observable through image textures)
-            s.v = 1.0 - dm::acos(s.normal.y) / HNM_PI;
+            s.v = 1.0 - ((FAST && HNM_FAST_ACOS) ? (double)acosf((float)s.normal.y) : dm::acos(s.normal.y)) / HNM_PI;
             double xz_len = __dsqrt_rn(s.normal.x * s.normal.x + s.normal.z * s.normal.z);
-            s.u = 0.5 - signum(s.normal.z) * dm::acos(s.normal.x / xz_len) / HNM_PI2;
+            s.u = 0.5 - signum(s.normal.z) * ((FAST && HNM_FAST_ACOS) ? (double)acosf((float)(s.normal.x / xz_len)) : dm::acos(s.normal.x / xz_len)) / HNM_PI2;
         }
     } else {  // cuboid, src/scene.rs:156-181
         const DElement& e = sc.elements[h.id];
@@ -499,12 +534,13 @@ HNM_D SurfacePoint surface_point(const DScene& sc, const Hit& h, D3 o, D3 dir, b
     return s;
 }
 // src/scene.rs:389-395
+template <bool FAST = false>
 HNM_D PointMaterial resolve_material(const DScene& sc, const DMaterial& m, double u, double v) {
     PointMaterial pm;
     pm.surface = m.surface; pm.param = m.param;
-    pm.albedo = texture_sample(sc, m.albedo, u, v);
-    pm.emission = texture_sample(sc, m.emission, u, v);
-    pm.roughness = texture_sample(sc, m.roughness, u, v).x;
+    pm.albedo = texture_sample<FAST>(sc, m.albedo, u, v);
+    pm.emission = texture_sample<FAST>(sc, m.emission, u, v);
+    pm.roughness = texture_sample<FAST>(sc, m.roughness, u, v).x;
     return pm;
 }
 

@@ -494,6 +494,7 @@ HNM_D Rand2 bounce_random(const RParams& P, uint32_t pid, int bounce) {
 #ifndef HNM_NEER_MIN_BLOCKS
 #define HNM_NEER_MIN_BLOCKS 4  /* 64 registers: 0.70 -> 0.60 ms */
 #endif
+template <bool FAST>
 __global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams P, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_MISS];
     uint32_t* const work = &P.counters[bounce * C_STRIDE + C_W_MISS];
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams
         uint32_t pid = P.pin[q];
         D3 d = load_ray_d(P, q);
         D3 thr = load_thr(P, q);
-        D3 emission = skybox_sample(P.sc, d);  // src/scene.rs:398
+        D3 emission = skybox_sample<FAST>(P.sc, d);  // src/scene.rs:398
         // accumulation += reflectance * emission (src/renderer.rs:196); the path ends (!hit, :199)
         D3 L = d3(P.L[0][pid], P.L[1][pid], P.L[2][pid]);
         L = L + thr * emission;
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams
 #ifndef HNM_SHADE_MIN_BLOCKS
 #define HNM_SHADE_MIN_BLOCKS 4  /* 64 registers (spills to local memory): measured best of 2 / 3 / 4 / 5 / 6 */
 #endif
-template <bool NEE>
+template <bool NEE, bool FAST>
 __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParams P, int bounce) {
     const int cls = NEE ? C_NEE : C_DELTA;
     note_warp_slot(P.dbg, 2);
@@ -570,10 +571,18 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
             h.kind = hid.x; h.id = hid.y;
             uint32_t el = h.kind == LEAF_TRI ? P.sc.tri_elem[h.id] : h.id;
             const DMaterial& dm_ = P.sc.materials[P.sc.elements[el].material];
-            sp = surface_point(P.sc, h, o, d, dm_.has_image != 0);
-            pm = resolve_material(P.sc, dm_, sp.u, sp.v);
+            sp = surface_point<FAST>(P.sc, h, o, d, dm_.has_image != 0);
+            pm = resolve_material<FAST>(P.sc, dm_, sp.u, sp.v);
             random = bounce_random(P, pid, bounce);
-            if (pm.surface != HNM_SURFACE_SPECULAR && pm.surface != HNM_SURFACE_REFRACTION) dm::sincos(HNM_PI2 * random.r0, sin_phi, cos_phi);
+            if (pm.surface != HNM_SURFACE_SPECULAR && pm.surface != HNM_SURFACE_REFRACTION) {
+                if (FAST && HNM_FAST_SINCOS) {
+                    float sf, cf;
+                    sincosf((float)(HNM_PI2 * random.r0), &sf, &cf);
+                    sin_phi = sf; cos_phi = cf;
+                } else {
+                    dm::sincos(HNM_PI2 * random.r0, sin_phi, cos_phi);
+                }
+            }
             view = -d;
             SampleResult res;
             bool some = material_sample(P.sc, pm, random, cos_phi, sin_phi, sp.position, view, sp.normal, res);
@@ -641,7 +650,7 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
 // src/renderer.rs:282-295 + :183,196 for the NEE events of one bounce, after k_trace listed the candidates of their
 // shadow rays: exact closest hit of every shadow ray (confirm_ray -- its only consumer is right here, so no hit record
 // goes through memory), visibility test, light contribution, radiance update.
-template <bool STATS>
+template <bool STATS, bool FAST>
 __global__ void __launch_bounds__(256, HNM_NEER_MIN_BLOCKS) k_nee_resolve(RParams P, CandLists cand, int bounce) {
     const uint32_t n = P.counters[bounce * C_STRIDE + C_EVENTS];
     const uint32_t nl = P.sc.num_emissions;
@@ -678,8 +687,8 @@ __global__ void __launch_bounds__(256, HNM_NEER_MIN_BLOCKS) k_nee_resolve(RParam
                 const DMaterial& hm = sc.materials[sc.elements[el].material];
                 D3 emission;
                 if (hm.emission.image >= 0) {
-                    SurfacePoint sp = surface_point(sc, h, o, d, true);
-                    emission = texture_sample(sc, hm.emission, sp.u, sp.v);
+                    SurfacePoint sp = surface_point<FAST>(sc, h, o, d, true);
+                    emission = texture_sample<FAST>(sc, hm.emission, sp.u, sp.v);
                 } else {
                     emission = d3(hm.emission.r, hm.emission.g, hm.emission.b);
                 }

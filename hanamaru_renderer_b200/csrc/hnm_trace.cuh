@@ -552,5 +552,123 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ k_confirm, TMA-staged (A/B)
+// The same kernel with its streaming inputs -- the six ray arrays and the four list-header arrays of 256 consecutive rays
+// -- staged into shared memory by 1-D bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes), double buffered: one
+// thread arms an mbarrier with the byte count and issues ten copies for the NEXT 256 rays while the CTA works on the
+// current ones.  `north_star` asks for TMA staging; this is where it applies on this path (contiguous SoA runs; the tree
+// itself is reached by per-lane gathers, which a bulk copy cannot express).  HNM_CONFIRM_TMA=1 selects it; DESIGN.md has
+// the measured A/B.  It needs 32 KB of shared memory per CTA, which cannot co-reside with the generation kernel's 224 KB.
+HNM_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+HNM_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+HNM_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+HNM_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+HNM_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "HNM_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra HNM_DONE_%=;\n"
+        "bra HNM_WAIT_%=;\n"
+        "HNM_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+template <bool STATS>
+__global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm_tma(DScene sc, TraceArgs A) {
+    constexpr int CH = 256;
+    __shared__ __align__(128) double s_ray[2][6][CH];
+    __shared__ __align__(128) uint32_t s_n[2][CH];
+    __shared__ __align__(128) float s_ub[2][CH];
+    __shared__ __align__(128) uint32_t s_id0[2][CH];
+    __shared__ __align__(128) float s_lo0[2][CH];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_base[2];
+    const int lane = threadIdx.x & 31;
+    const TraceJob& J = A.job[0];
+    const uint32_t ntot = *J.count;
+    uint32_t n_prims = 0;
+    const bool classify = J.q_miss != nullptr;
+    // one thread: claim the next 256 rays and start their ten copies into stage `st`
+    auto prefetch = [&](int st) {
+        const uint32_t base = atomicAdd(A.work_confirm, (uint32_t)CH);
+        s_base[st] = base;
+        if (base >= ntot) return;
+        const uint32_t cnt = ((ntot - base < (uint32_t)CH ? ntot - base : (uint32_t)CH) + 3u) & ~3u;  // 16-byte multiples (arrays are padded)
+        mbar_expect_tx(&s_bar[st], cnt * (6u * 8u + 4u * 4u));
+        const uint32_t slot = J.slot0 + base;
+        for (int k = 0; k < 6; k++) bulk_g2s(&s_ray[st][k][0], J.ray[k] + base, cnt * 8u, &s_bar[st]);
+        bulk_g2s(&s_n[st][0], A.cand.n + slot, cnt * 4u, &s_bar[st]);
+        bulk_g2s(&s_ub[st][0], A.cand.ub + slot, cnt * 4u, &s_bar[st]);
+        bulk_g2s(&s_id0[st][0], A.cand.id + slot, cnt * 4u, &s_bar[st]);
+        bulk_g2s(&s_lo0[st][0], A.cand.lo + slot, cnt * 4u, &s_bar[st]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        prefetch(0);
+    }
+    __syncthreads();
+    for (uint32_t it = 0;; it++) {
+        const int st = it & 1;
+        if (threadIdx.x == 0) prefetch(st ^ 1);  // stage st^1 was released by the barrier that ended the previous iteration
+        const uint32_t base = s_base[st];
+        if (base >= ntot) break;                 // CTA-uniform: s_base[st] was published before the last barrier
+        mbar_wait(&s_bar[st], (it >> 1) & 1u);
+        const uint32_t idx = base + threadIdx.x;
+        int cls = -1;
+        if (idx < ntot) {
+            const uint32_t q = idx, slot = J.slot0 + q;
+            const uint32_t n = s_n[st][threadIdx.x];
+            if (STATS && n == CAND_OVERFLOW) atomicAdd(&A.stats[6], 1ull);
+            const D3 o = d3(s_ray[st][0][threadIdx.x], s_ray[st][1][threadIdx.x], s_ray[st][2][threadIdx.x]);
+            const D3 dir = d3(s_ray[st][3][threadIdx.x], s_ray[st][4][threadIdx.x], s_ray[st][5][threadIdx.x]);
+            const Hit best = confirm_ray<STATS>(sc, A.cand, slot, n, s_ub[st][threadIdx.x], s_id0[st][threadIdx.x], s_lo0[st][threadIdx.x], o, dir, n_prims);
+            __stcs(J.hit_t + q, best.t); __stcs(J.hit_u + q, best.u); __stcs(J.hit_v + q, best.v);
+            __stcs(J.hit_id + q, make_uint2(best.kind, best.id));
+            if (classify) {
+                if (best.kind == LEAF_NONE) cls = 0;
+                else {
+                    uint32_t el = best.kind == LEAF_TRI ? sc.tri_elem[best.id] : best.id;
+                    int surface = sc.materials[sc.elements[el].material].surface;
+                    cls = nee_available(surface) ? 2 : 1;
+                }
+            }
+        }
+        if (classify) {
+            const unsigned m0 = __ballot_sync(0xFFFFFFFFu, cls == 0), m1 = __ballot_sync(0xFFFFFFFFu, cls == 1), m2 = __ballot_sync(0xFFFFFFFFu, cls == 2);
+            uint32_t b = 0;
+            if (lane < 3) {
+                const unsigned m = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+                uint32_t* ctr = lane == 0 ? J.cnt_miss : (lane == 1 ? J.cnt_delta : J.cnt_nee);
+                if (m) b = atomicAdd(ctr, (uint32_t)__popc(m));
+            }
+            const uint32_t b0 = __shfl_sync(0xFFFFFFFFu, b, 0), b1 = __shfl_sync(0xFFFFFFFFu, b, 1), b2 = __shfl_sync(0xFFFFFFFFu, b, 2);
+            if (cls >= 0) {
+                const unsigned m = cls == 0 ? m0 : (cls == 1 ? m1 : m2);
+                uint32_t* q = cls == 0 ? J.q_miss : (cls == 1 ? J.q_delta : J.q_nee);
+                q[(cls == 0 ? b0 : (cls == 1 ? b1 : b2)) + __popc(m & ((1u << lane) - 1u))] = idx;
+            }
+        }
+        __syncthreads();  // stage st may be refilled, s_base[st^1] is visible
+    }
+    if (STATS) {
+        for (int s = 16; s > 0; s >>= 1) n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, s);
+        if (lane == 0) atomicAdd(&A.stats[A.stat_prims], (unsigned long long)n_prims);
+    }
+}
+
 }  // namespace hnm
 #endif

@@ -259,6 +259,13 @@ int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t samplin
  * the device) into image row order. */
 int hnm_deinterleave(hnm_renderer* r, const void* gathered_device, void* full_device);
 
+/* Precision of the shading kernels.  EXACT (default): every operation is the reference's f64 sequence, transcendental
+ * functions from the deterministic library -- bit parity with the oracle.  FAST_MATH (opt-in): pow / sincos / acos of the
+ * shading kernels in hardware f32; traversal, exact hit tests, RNG and accumulation are unchanged.  Results are then
+ * statistically equal (tests: PSNR >= 45 dB and mean bias < 0.5 level against the oracle at equal spp and seed). */
+enum { HNM_PRECISION_EXACT = 0, HNM_PRECISION_FAST_MATH = 1 };
+int hnm_set_precision(hnm_renderer* r, int precision);
+
 int hnm_get_counters(hnm_renderer* r, hnm_counters* out);
 /* ms of device time spent in the top kernels since the last reset (CUDA
  * events on the renderer's stream); names are static strings. */

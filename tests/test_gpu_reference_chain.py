@@ -78,3 +78,34 @@ def test_other_scenes_vs_platform_libm(hr, core, oracle_glibc, get_scene, get_de
     want, _ = oracle_glibc.render(scene, w, h, hr.MODE_PATHTRACING, 1, 2, counters=False)
     outliers, n = compare(got, want, "GPU vs glibc oracle, %s %dx%d -s 2" % (name, w, h))
     assert outliers <= 2e-3 * n
+
+
+def test_fast_math_mode_statistical_acceptance(hr, core, oracle, get_scene, get_device_scene):
+    """The opt-in perf mode (hnm_set_precision FAST_MATH: pow / sincos / acos of the shading kernels in hardware f32) against
+    the oracle at EQUAL spp and seed -- SURVEY 8(c) acceptance 5: u8 image PSNR >= 45 dB, mean per-channel bias < 0.5 level.
+    (The default mode stays bit-exact; this mode is never what the parity tests or the default bench run.)"""
+    from hanamaru_renderer_b200 import _ffi
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    w, h, passes = 480, 270, 16
+    ctx = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING)
+    ctx.set_precision(_ffi.PRECISION_FAST_MATH)
+    ctx.render_passes(1, passes)
+    ctx.synchronize()
+    img = ctx.resolve(passes).astype(np.float64)
+    acc = ctx.read_accum()
+    ctx.set_precision(_ffi.PRECISION_EXACT)
+    ctx.clear()
+    ctx.render_passes(1, passes)
+    ctx.synchronize()
+    exact = ctx.read_accum()
+    ctx.close()
+    want, _ = oracle.render(scene, w, h, hr.MODE_PATHTRACING, 1, passes, counters=False)
+    assert np.array_equal(exact.view(np.uint64), want.view(np.uint64))   # switching back restores bit parity
+    want_img = oracle.resolve(scene.desc.contents.config, want, passes).astype(np.float64)
+    mse = float(((img - want_img) ** 2).mean())
+    psnr = 10 * np.log10(255.0 ** 2 / mse) if mse > 0 else 99.0
+    bias = (img - want_img).mean(axis=(0, 1))
+    rel = np.linalg.norm(acc - want, axis=2) / np.maximum(np.linalg.norm(want, axis=2), 1e-300)
+    print("FAST_MATH vs oracle, %dx%d x %d passes: PSNR %.2f dB, mean bias per channel %s, median relative HDR error %.3g, pixels above 1e-3: %d"
+          % (w, h, passes, psnr, np.round(bias, 4).tolist(), float(np.median(rel)), int((rel > 1e-3).sum())))
+    assert psnr >= 45.0 and np.abs(bias).max() < 0.5

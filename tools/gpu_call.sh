@@ -77,6 +77,11 @@ d=json.loads(sys.stdin.read()); print('  config2', round(d['value'],1), 'ms/pass
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config4', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"
                done; } > $OUT/abdyn.log 2>&1; cat $OUT/abdyn.log ;;
+    fast)    { timeout 600 python -m pytest tests/test_gpu_reference_chain.py -k fast_math -m gpu -q -s 2>&1 | grep "FAST_MATH\|passed\|failed";
+               for prec in exact fast; do for c in 2 4; do timeout 300 python bench.py --config $c --steps 4 --precision $prec --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('$prec config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3), {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items() if k in ('shade_miss','shade_delta','shade_nee','nee_resolve')})"; done; done; } > $OUT/fast.log 2>&1; cat $OUT/fast.log ;;
+    edge2)   timeout 900 python -m pytest tests/test_gpu_edge_cases.py -k directed -m gpu -q -s -rf 2>&1 | grep "directed rays\|passed\|failed" > $OUT/edge2.log; cat $OUT/edge2.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
