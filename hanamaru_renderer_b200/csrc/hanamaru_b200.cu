@@ -60,6 +60,7 @@ struct hnm_renderer {
     uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
     bool profiling = false, trace_stats = false, per_bounce_names = false, wid_stats = false;
     bool profile_overlap = false;
+    int isaac_rounds = 0;          // HNM_ISAAC_ROUNDS=k: generation CTAs of k rounds (k x 112 paths) instead of one persistent CTA per SM
     bool confirm_tma = false;      // HNM_CONFIRM_TMA=1: the TMA-staged k_confirm (A/B)
     bool fast_math = false;        // hnm_set_precision(HNM_PRECISION_FAST_MATH): opt-in, statistical parity only
     bool rng_midtrace = false;     // HNM_RNG_MIDTRACE=1: the prefetch is enqueued right behind a trace launch, without waiting for it
@@ -181,7 +182,13 @@ int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, 
     G.pout = g.pid;
     HNM_CUDA(cudaMemsetAsync(g.ovf_counter, 0, sizeof(uint32_t), on));
     size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
-    launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<r->sm_count, ISAAC_THREADS, smem, on>>>(G); }, on);
+    // Grid: one persistent CTA per SM, or (isaac_rounds > 0) short-lived CTAs of `isaac_rounds` x 112 paths.  The SM's issue
+    // arbiter serves the OLDEST resident warps first (tools/microbench/prio.cu): a persistent generation CTA outranks every
+    // kernel launched after it, short-lived ones are younger than the persistent k_trace CTAs they run next to.
+    int igrid = r->sm_count;
+    if (r->isaac_rounds > 0 && on == r->rng_stream)
+        igrid = (int)std::max<uint64_t>(r->sm_count, ((uint64_t)G.N + (uint64_t)ISAAC_PATHS * r->isaac_rounds - 1) / ((uint64_t)ISAAC_PATHS * r->isaac_rounds));
+    launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<igrid, ISAAC_THREADS, smem, on>>>(G); }, on);
     launch_timed(r, "rng_overflow", [&] { k_rng_overflow<<<r->sm_count, 64, 0, on>>>(G); }, on);
     g.valid = true;
     g.sampling_first = sampling_first;
@@ -513,6 +520,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
+    if (const char* e = getenv("HNM_ISAAC_ROUNDS")) r->isaac_rounds = std::max(0, atoi(e));
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_RNG_SPECULATE")) r->speculate = atoi(e) != 0;
@@ -839,9 +847,10 @@ int hnm_group_create(const hnm_scene_desc* desc, const hnm_camera* camera, uint3
     *out = nullptr;
     if (num_devices == 0 || num_devices > 64) return set_error(HNM_ERR_INVALID, "bad device count");
     if (tile_rows == 0) tile_rows = 4;
-    SceneBuilder b(desc);
-    int rc = scene_build_host(desc, b);  // validated and re-laid out ONCE, uploaded to every device
+    std::shared_ptr<SceneBuilder> bp;
+    int rc = scene_build_cached(desc, bp);  // validated and re-laid out ONCE, uploaded to every device
     if (rc) return rc;
+    const SceneBuilder& b = *bp;
     hnm_group* g = new hnm_group();
     g->W = width; g->H = height;
     auto bail = [&](int code) { hnm_group_destroy(g); return code; };

@@ -6,9 +6,12 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -52,7 +55,7 @@ struct BoxD {
     void grow(const BoxD& o) {
         if (o.empty) return;
         if (empty) { *this = o; return; }
-        for (int k = 0; k < 3; k++) { lo[k] = std::fmin(lo[k], o.lo[k]); hi[k] = std::fmax(hi[k], o.hi[k]); }
+        for (int k = 0; k < 3; k++) { lo[k] = o.lo[k] < lo[k] ? o.lo[k] : lo[k]; hi[k] = o.hi[k] > hi[k] ? o.hi[k] : hi[k]; }
     }
 };
 inline BoxD box_of(const double* mn, const double* mx) {
@@ -286,6 +289,7 @@ class SceneBuilder {
     uint32_t depth = 0;
 
     std::vector<uint32_t> tri_order;  // traversal (leaf) position -> triangle index in the reference's leaf order
+    void detach() { d_ = nullptr; }   // a cached build outlives the caller's description: only the result vectors remain valid
 
   private:
     const hnm_scene_desc* d_;
@@ -307,13 +311,19 @@ class SceneBuilder {
         out = BoxD();
         BoxD cb;  // centroid bounds
         bool all_tri = true;
-        for (size_t i = lo; i < hi; i++) {
-            out.grow(prims[i].box);
-            BoxD c;
-            c.empty = false;
-            for (int k = 0; k < 3; k++) c.lo[k] = c.hi[k] = prims[i].c[k];
-            cb.grow(c);
-            all_tri = all_tri && prims[i].kind == LEAF_TRI;
+        {
+            double ol[3] = {INFINITY, INFINITY, INFINITY}, oh[3] = {-INFINITY, -INFINITY, -INFINITY};
+            double cl[3] = {INFINITY, INFINITY, INFINITY}, ch[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (size_t i = lo; i < hi; i++) {
+                const Prim& p = prims[i];
+                for (int k = 0; k < 3; k++) {
+                    ol[k] = p.box.lo[k] < ol[k] ? p.box.lo[k] : ol[k]; oh[k] = p.box.hi[k] > oh[k] ? p.box.hi[k] : oh[k];
+                    cl[k] = p.c[k] < cl[k] ? p.c[k] : cl[k]; ch[k] = p.c[k] > ch[k] ? p.c[k] : ch[k];
+                }
+                all_tri = all_tri && p.kind == LEAF_TRI;
+            }
+            out.empty = cb.empty = hi <= lo;
+            for (int k = 0; k < 3; k++) { out.lo[k] = ol[k]; out.hi[k] = oh[k]; cb.lo[k] = cl[k]; cb.hi[k] = ch[k]; }
         }
         const size_t n = hi - lo;
         auto make_leaf = [&]() -> int32_t {
@@ -323,44 +333,77 @@ class SceneBuilder {
             return leaf_link(LEAF_TRI, (uint32_t)n, first);
         };
         if (n == 1) return make_leaf();
-        // best binned split over the three axes
-        const int NB = 32;
+        // best binned split over the three axes: ONE pass over the primitives fills the bins of all three axes (plain
+        // min / max on +-inf-initialised boxes; the bin index is a multiply, and std::partition below uses the same
+        // expression).  This loop is the host-side cost of hnm_scene_create: 44 -> ~15 ms for the 12 k-triangle default scene.
+        const int NBMAX = 32;
+        const int NB = n >= 64 ? 32 : (n >= 16 ? 16 : 8);  // the fixed cost per node (bin set-up + sweeps) dominates small nodes
         double best_cost = 1e300;
         int best_axis = -1, best_bin = -1;
         const double parent_area = std::fmax(half_area(out), 1e-300);
+        double scale[3];
+        bool use_axis[3];
         for (int axis = 0; axis < 3; axis++) {
-            double ext = cb.hi[axis] - cb.lo[axis];
-            if (!(ext > 0.0)) continue;
-            BoxD bb[NB];
-            size_t cnt[NB] = {0};
-            for (size_t i = lo; i < hi; i++) {
-                int b = (int)((prims[i].c[axis] - cb.lo[axis]) / ext * NB);
-                b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
-                bb[b].grow(prims[i].box);
-                cnt[b]++;
+            const double ext = cb.hi[axis] - cb.lo[axis];
+            use_axis[axis] = ext > 0.0;
+            scale[axis] = use_axis[axis] ? (double)NB / ext : 0.0;
+        }
+        struct Bin { double lo[3], hi[3]; size_t cnt; };
+        Bin bins[3][NBMAX];
+        for (int axis = 0; axis < 3; axis++)
+            for (int k = 0; k < NB; k++) {
+                Bin& bn = bins[axis][k];
+                bn.lo[0] = bn.lo[1] = bn.lo[2] = INFINITY; bn.hi[0] = bn.hi[1] = bn.hi[2] = -INFINITY; bn.cnt = 0;
             }
-            double right_area[NB];
-            size_t right_cnt[NB];
-            BoxD acc;
+        for (size_t i = lo; i < hi; i++) {
+            const Prim& p = prims[i];
+            for (int axis = 0; axis < 3; axis++) {
+                if (!use_axis[axis]) continue;
+                int k = (int)((p.c[axis] - cb.lo[axis]) * scale[axis]);
+                k = k < 0 ? 0 : (k >= NB ? NB - 1 : k);
+                Bin& bn = bins[axis][k];
+                for (int c = 0; c < 3; c++) {
+                    bn.lo[c] = p.box.lo[c] < bn.lo[c] ? p.box.lo[c] : bn.lo[c];
+                    bn.hi[c] = p.box.hi[c] > bn.hi[c] ? p.box.hi[c] : bn.hi[c];
+                }
+                bn.cnt++;
+            }
+        }
+        auto area_of = [](const double* l, const double* h) {
+            const double dx = h[0] - l[0], dy = h[1] - l[1], dz = h[2] - l[2];
+            return dx * dy + dy * dz + dz * dx;
+        };
+        for (int axis = 0; axis < 3; axis++) {
+            if (!use_axis[axis]) continue;
+            double right_area[NBMAX];
+            size_t right_cnt[NBMAX];
+            double l[3] = {INFINITY, INFINITY, INFINITY}, h[3] = {-INFINITY, -INFINITY, -INFINITY};
             size_t c = 0;
-            for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); c += cnt[b]; right_area[b] = half_area(acc); right_cnt[b] = c; }
-            acc = BoxD();
+            for (int k = NB - 1; k > 0; k--) {
+                const Bin& bn = bins[axis][k];
+                for (int t = 0; t < 3; t++) { l[t] = bn.lo[t] < l[t] ? bn.lo[t] : l[t]; h[t] = bn.hi[t] > h[t] ? bn.hi[t] : h[t]; }
+                c += bn.cnt;
+                right_area[k] = c ? area_of(l, h) : 0.0;
+                right_cnt[k] = c;
+            }
+            l[0] = l[1] = l[2] = INFINITY; h[0] = h[1] = h[2] = -INFINITY;
             c = 0;
-            for (int b = 0; b < NB - 1; b++) {
-                acc.grow(bb[b]);
-                c += cnt[b];
-                if (c == 0 || right_cnt[b + 1] == 0) continue;
-                double cost = 1.0 + sah_ct * (half_area(acc) * (double)c + right_area[b + 1] * (double)right_cnt[b + 1]) / parent_area;
-                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            for (int k = 0; k < NB - 1; k++) {
+                const Bin& bn = bins[axis][k];
+                for (int t = 0; t < 3; t++) { l[t] = bn.lo[t] < l[t] ? bn.lo[t] : l[t]; h[t] = bn.hi[t] > h[t] ? bn.hi[t] : h[t]; }
+                c += bn.cnt;
+                if (c == 0 || right_cnt[k + 1] == 0) continue;
+                const double cost = 1.0 + sah_ct * (area_of(l, h) * (double)c + right_area[k + 1] * (double)right_cnt[k + 1]) / parent_area;
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = k; }
             }
         }
         const double leaf_cost = sah_ct * (double)n;  // cost of one triangle pre-test in node steps
         if (all_tri && n <= sah_max_leaf && (best_axis < 0 || leaf_cost <= best_cost)) return make_leaf();
         size_t mid;
         if (best_axis >= 0) {
-            double ext = cb.hi[best_axis] - cb.lo[best_axis], base = cb.lo[best_axis];
+            const double base = cb.lo[best_axis], sc_ = scale[best_axis];
             auto it = std::partition(prims.begin() + lo, prims.begin() + hi, [&](const Prim& p) {
-                int b = (int)((p.c[best_axis] - base) / ext * NB);
+                int b = (int)((p.c[best_axis] - base) * sc_);
                 b = b < 0 ? 0 : (b >= NB ? NB - 1 : b);
                 return b <= best_bin;
             });
@@ -534,19 +577,90 @@ inline void scene_free(hnm_scene* s) {
 
 // host part of hnm_scene_create: validation + re-layout (no CUDA call); one build serves every device of a group
 inline int scene_build_host(const hnm_scene_desc* desc, SceneBuilder& b) {
+    const bool timing = getenv("HNM_BUILD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (!b.validate()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    const double t1 = now();
     if (!b.build()) return set_error(HNM_ERR_INVALID, "scene description: " + b.error);
+    if (timing) fprintf(stderr, "hnm_scene_create host part: validate %.2f ms, build %.2f ms (%zu nodes, depth %u)\n", t1 - t0, now() - t1, b.nodes.size(), b.depth);
     (void)desc;
     return 0;
 }
 inline int scene_upload(const hnm_scene_desc* desc, const SceneBuilder& b, int device, hnm_scene** out);
+
+// The re-layout depends on the geometry arrays and the two trees only.  A host that calls Renderer::render again with the
+// same scene (progress renders, the debug pass after the main pass, one scene copy per device) gets the previous build
+// back: a 64-bit content hash of those arrays (and of the environment knobs the builder reads) keys a small cache.
+inline uint64_t hash_bytes(uint64_t h, const void* p, size_t n) {
+    const uint8_t* b = (const uint8_t*)p;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t v;
+        memcpy(&v, b + i, 8);
+        h = (h ^ v) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; i < n; i++) h = (h ^ b[i]) * 0x100000001B3ull;
+    return h;
+}
+inline uint64_t scene_geometry_hash(const hnm_scene_desc* d) {
+    uint64_t h = 0xCBF29CE484222325ull;
+    auto arr = [&](const void* p, size_t n) { uint64_t sz = n; h = hash_bytes(h, &sz, 8); if (p && n) h = hash_bytes(h, p, n); };
+    arr(d->elements, (size_t)d->num_elements * sizeof(hnm_element));
+    arr(d->meshes, (size_t)d->num_meshes * sizeof(hnm_mesh));
+    arr(d->vertices, (size_t)d->num_vertices * 24);
+    arr(d->faces, (size_t)d->num_faces * 12);
+    arr(d->mesh_nodes, (size_t)d->num_mesh_nodes * sizeof(hnm_bvh_node));
+    arr(d->mesh_indices, (size_t)d->num_mesh_indices * 4);
+    arr(d->top_nodes, (size_t)d->num_top_nodes * sizeof(hnm_bvh_node));
+    arr(d->top_indices, (size_t)d->num_top_indices * 4);
+    for (const char* k : {"HNM_BVH", "HNM_SAH_CT", "HNM_SAH_MAXLEAF", "HNM_CHAIN_FULL"}) {
+        const char* v = getenv(k);
+        arr(v ? v : "", v ? strlen(v) : 0);
+    }
+    return h;
+}
+struct BuildCache {
+    std::mutex m;
+    std::vector<std::pair<uint64_t, std::shared_ptr<SceneBuilder>>> entries;  // most recent last, at most 4
+};
+inline BuildCache& build_cache() { static BuildCache c; return c; }
+// validated + built description, from the cache when the same geometry was built before
+inline int scene_build_cached(const hnm_scene_desc* desc, std::shared_ptr<SceneBuilder>& out) {
+    if (!desc) return set_error(HNM_ERR_INVALID, "scene description: null scene description");
+    {
+        // validation always runs (it covers the parts of the description that are not hashed: materials, images, config)
+        SceneBuilder v(desc);
+        if (!v.validate()) return set_error(HNM_ERR_INVALID, "scene description: " + v.error);
+    }
+    const bool use_cache = !getenv("HNM_BUILD_CACHE") || atoi(getenv("HNM_BUILD_CACHE")) != 0;
+    const uint64_t key = scene_geometry_hash(desc);
+    BuildCache& c = build_cache();
+    if (use_cache) {
+        std::lock_guard<std::mutex> g(c.m);
+        for (auto& e : c.entries)
+            if (e.first == key) { out = e.second; return 0; }
+    }
+    auto b = std::make_shared<SceneBuilder>(desc);
+    int rc = scene_build_host(desc, *b);
+    if (rc) return rc;
+    b->detach();
+    if (use_cache) {
+        std::lock_guard<std::mutex> g(c.m);
+        c.entries.emplace_back(key, b);
+        if (c.entries.size() > 4) c.entries.erase(c.entries.begin());
+    }
+    out = b;
+    return 0;
+}
 inline int scene_create(const hnm_scene_desc* desc, int device, hnm_scene** out) {
     if (!out) return set_error(HNM_ERR_INVALID, "null output pointer");
     *out = nullptr;
-    SceneBuilder b(desc);
-    int rc = scene_build_host(desc, b);
+    std::shared_ptr<SceneBuilder> b;
+    int rc = scene_build_cached(desc, b);
     if (rc) return rc;
-    return scene_upload(desc, b, device, out);
+    return scene_upload(desc, *b, device, out);
 }
 inline int scene_upload(const hnm_scene_desc* desc, const SceneBuilder& b, int device, hnm_scene** out) {
     *out = nullptr;

@@ -82,6 +82,30 @@ d=json.loads(sys.stdin.read()); print('  config4', round(d['value'],1), 'ms/pass
 import json,sys
 d=json.loads(sys.stdin.read()); print('$prec config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3), {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items() if k in ('shade_miss','shade_delta','shade_nee','nee_resolve')})"; done; done; } > $OUT/fast.log 2>&1; cat $OUT/fast.log ;;
     edge2)   timeout 900 python -m pytest tests/test_gpu_edge_cases.py -k directed -m gpu -q -s -rf 2>&1 | grep "directed rays\|passed\|failed" > $OUT/edge2.log; cat $OUT/edge2.log ;;
+    tma)     { for sc in rtcamp6 bvh_heavy; do for e in 0 1; do echo "== $sc HNM_CONFIRM_TMA=$e";
+                 HNM_CONFIRM_TMA=$e timeout 200 python tools/diag_scene.py $sc 160 90 1 2 2>&1 | tail -1 | cut -c1-90
+                 HNM_CONFIRM_TMA=$e HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 6 2>&1 | tail -2; done; done; } > $OUT/tma.log 2>&1; cat $OUT/tma.log ;;
+    prof)    RND=r02
+             timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$RND.csv python bench.py --steps 2 --warmup 3 --pps 1 --no-e2e --no-cpu --no-traffic > $OUT/prof_bench.log 2>&1
+             export HNM_RNG_OVERLAP=0
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/prof_trace_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p1.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/prof_trace3_$RND python tools/traffic_probe.py bvh_heavy 1920 1080 > $OUT/p2.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirm_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p3.log 2>&1
+             HNM_CONFIRM_TMA=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirmtma_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p4.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen -c 1 -f -o gpurun_out/prof_isaac_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p5.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade_surf -c 2 -f -o gpurun_out/prof_shade_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p6.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nee_resolve -c 1 -f -o gpurun_out/prof_neer_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p7.log 2>&1
+             ls -la gpurun_out/*$RND* ;;
+    young)   { for e in "HNM_X=0" "HNM_ISAAC_ROUNDS=1" "HNM_ISAAC_ROUNDS=1 HNM_RNG_START_BOUNCE=0" \
+                 "HNM_CORE_LIB=_variants/isaac64r.so HNM_TRACE_BLOCKS=7" \
+                 "HNM_CORE_LIB=_variants/isaac64r.so HNM_TRACE_BLOCKS=7 HNM_ISAAC_ROUNDS=1" \
+                 "HNM_CORE_LIB=_variants/isaac64r.so HNM_TRACE_BLOCKS=7 HNM_ISAAC_ROUNDS=1 HNM_RNG_START_BOUNCE=0" \
+                 "HNM_CORE_LIB=_variants/isaac64r.so HNM_TRACE_BLOCKS=7 HNM_ISAAC_ROUNDS=4 HNM_RNG_START_BOUNCE=0" \
+                 "HNM_CORE_LIB=_variants/isaac64r.so HNM_TRACE_BLOCKS=6 HNM_ISAAC_ROUNDS=1 HNM_RNG_START_BOUNCE=0"; do
+                 echo "== $e"
+                 for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 6 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/young.log 2>&1; cat $OUT/young.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
