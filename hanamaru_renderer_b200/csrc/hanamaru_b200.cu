@@ -60,6 +60,7 @@ struct hnm_renderer {
     uint8_t* rgb8_host = nullptr;  // pinned staging of the resolved image (the caller's buffer is pageable)
     bool profiling = false, trace_stats = false, per_bounce_names = false, wid_stats = false;
     bool profile_overlap = false;
+    bool isaac_tmem = true;        // generation through the TMEM pipeline (k_isaac_raygen_tm); HNM_ISAAC_TMEM=0: k_isaac_raygen
     int isaac_rounds = 0;          // HNM_ISAAC_ROUNDS=k: generation CTAs of k rounds (k x 112 paths) instead of one persistent CTA per SM
     bool confirm_tma = false;      // HNM_CONFIRM_TMA=1: the TMA-staged k_confirm (A/B)
     bool fast_math = false;        // hnm_set_precision(HNM_PRECISION_FAST_MATH): opt-in, statistical parity only
@@ -188,7 +189,10 @@ int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, 
     int igrid = r->sm_count;
     if (r->isaac_rounds > 0 && on == r->rng_stream)
         igrid = (int)std::max<uint64_t>(r->sm_count, ((uint64_t)G.N + (uint64_t)ISAAC_PATHS * r->isaac_rounds - 1) / ((uint64_t)ISAAC_PATHS * r->isaac_rounds));
-    launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<igrid, ISAAC_THREADS, smem, on>>>(G); }, on);
+    if (r->isaac_tmem)
+        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen_tm<<<r->sm_count, ISAAC_TM_THREADS, smem, on>>>(G); }, on);
+    else
+        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<igrid, ISAAC_THREADS, smem, on>>>(G); }, on);
     launch_timed(r, "rng_overflow", [&] { k_rng_overflow<<<r->sm_count, 64, 0, on>>>(G); }, on);
     g.valid = true;
     g.sampling_first = sampling_first;
@@ -520,6 +524,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
+    if (const char* e = getenv("HNM_ISAAC_TMEM")) r->isaac_tmem = atoi(e) != 0;
     if (const char* e = getenv("HNM_ISAAC_ROUNDS")) r->isaac_rounds = std::max(0, atoi(e));
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
@@ -629,6 +634,8 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (ce == cudaSuccess && P.dbg) ce = cudaMemsetAsync(P.dbg, 0, 8 * sizeof(unsigned long long), r->stream);
     if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
         ce = cudaFuncSetAttribute(k_isaac_raygen, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_PATHS * 256 * (int)sizeof(uint64_t));
+    if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
+        ce = cudaFuncSetAttribute(k_isaac_raygen_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_PATHS * 256 * (int)sizeof(uint64_t));
     if (const char* e = getenv("HNM_CARVEOUT")) {
         // experiment: the shared-memory carve-out the kernels that co-reside with k_isaac_raygen ask for
         int c = atoi(e);
@@ -1077,8 +1084,14 @@ int hnm_isaac64_batch(int device, const uint64_t* seeds, uint32_t n, uint32_t co
     if ((rc = T.alloc(&dout, (size_t)n * count * sizeof(uint64_t)))) return rc;
     if (count <= HNM_RNG_TAIL) {
         size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
-        HNM_CUDA(cudaFuncSetAttribute(k_isaac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_isaac_batch<<<sms, ISAAC_THREADS, smem>>>(ds, n, count, dout);
+        const char* e = getenv("HNM_ISAAC_TMEM");
+        if (!e || atoi(e) != 0) {
+            HNM_CUDA(cudaFuncSetAttribute(k_isaac_batch_tm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_isaac_batch_tm<<<sms, ISAAC_TM_THREADS, smem>>>(ds, n, count, dout);
+        } else {
+            HNM_CUDA(cudaFuncSetAttribute(k_isaac_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_isaac_batch<<<sms, ISAAC_THREADS, smem>>>(ds, n, count, dout);
+        }
     } else {
         k_isaac_full_batch<<<sms, 64>>>(ds, n, count, dout);  // the exact slow path, with refill
     }

@@ -148,8 +148,9 @@ HNM_D PathCoord path_coord(const RParams& P, uint32_t p) {
 
 // `mem` is this thread's column of a [256][T] u64 array (shared memory: conflict-free for any per-lane
 // index because the bank depends only on the lane).  Outputs rsl[i] are handed to `sink`.
-template <int T, int KEEP, typename Sink>
-__device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, Sink sink) {
+// init(true) of rand 0.4.3: the two mixing passes over rsl = [s0 s1 s2 s3 0 0 ...] and then over mem itself
+template <int T>
+__device__ __forceinline__ void isaac64_init(uint64_t* mem, uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3) {
 #define MEM(i) mem[(i) * T]
     uint64_t a, b, c, d, e, f, g, h;
     a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
@@ -172,63 +173,251 @@ __device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_
         MEM(i) = a; MEM(i + 1) = b; MEM(i + 2) = c; MEM(i + 3) = d;
         MEM(i + 4) = e; MEM(i + 5) = f; MEM(i + 6) = g; MEM(i + 7) = h;
     }
-    // isaac64(): a = 0, b = 0, c = 1  ->  aa = 0, bb = 1
-    // One step:  x = mem[i];  aa = mix(aa) + mem[i ^ 128];  y = mem[ind(x)] + aa + bb;  mem[i] = y;
-    //            bb = mem[ind(y >> 8)] + x;  rsl[i] = bb.
-    // Written naively, the data-dependent load mem[ind(x)] of step i+1 must wait for the store mem[i] = y of step i
-    // (it may alias), and y waits for bb, which waits for the other data-dependent load: two shared-memory
-    // latencies per step on the critical chain.  Here x and mem[ind(x)] of the NEXT step are loaded before this
-    // step's store and the one possible alias (ind(x') == i) is patched by forwarding y: one latency per step.
-    uint64_t aa = 0, bb = 1;
-    // data-dependent addresses with one operation less on the dependent chain: byte offset of mem[(x >> 3) & 255] is
-    // (x & 0x7f8) * T, that of mem[(y >> 11) & 255] is the high word of (y & 0x7f800) * ((8 * T) << 21)
+#undef MEM
+}
+
+// Shared-memory accesses of the round are volatile PTX with compile-time offsets from a row register: their ORDER in the
+// instruction stream is the order written here (ptxas would otherwise sink the static-index loads next to their uses,
+// which a single in-order warp then waits for).
+template <int OFF>
+HNM_D uint64_t lds64v(uint32_t saddr) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(saddr), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+HNM_D void sts64v(uint32_t saddr, uint64_t v) {
+    asm volatile("st.volatile.shared.u64 [%0+%1], %2;" :: "r"(saddr), "n"(OFF), "l"(v) : "memory");
+}
+// The first isaac64() round after init: the 256 data-dependent steps over `mem` (this thread's column of [256][T] u64).
+//   One step:  x = mem[i];  aa = mix(aa) + mem[i ^ 128];  y = mem[ind(x)] + aa + bb;  mem[i] = y;
+//              bb = mem[ind(y >> 8)] + x;  rsl[i] = bb.
+// One warp per scheduler issues in order, so the step time is the dependent chain plus every stall the in-order stream
+// exposes.  The chain is  y -> address of mem[ind(y >> 8)] -> shared-memory load -> next y  and nothing else is on it:
+//   * bb only ever enters the next y, so the step carries the raw load `ldy` and y = p + ldy + s is ONE three-input
+//     addition behind it, with s = aa + x(previous) computed while the load is in flight;
+//   * the other data-dependent load, p = mem[ind(x)] of the NEXT step, is issued right behind this step's store
+//     (program order makes it see y if it aliases); its address was computed a step earlier from x, which is a
+//     static-index load of a word no earlier step has written and is fetched two steps ahead;
+//   * mem[i ^ 128] is fetched two steps ahead, so that aa and s of the NEXT step are computed in the shadow of this
+//     step's loads.
+// Round 1 loaded mem[ind(x)] BEFORE the store and patched the possible alias by forwarding y (a compare and two selects on
+// the chain): 28 instructions and 94 cycles per step; this form has 21 instructions.
+template <int T, int KEEP, typename Sink>
+__device__ __forceinline__ void isaac64_round(uint64_t* mem, Sink sink) {
     static_assert(8 * T < 2048, "the umulhi form needs (8 * T) << 21 to fit 32 bits");
-    const char* const memb = reinterpret_cast<const char*>(mem);
-#define MEMX(x) (*reinterpret_cast<const uint64_t*>(memb + ((uint32_t)(x) & 0x7f8u) * (uint32_t)T))
-#define MEMY(y) (*reinterpret_cast<const uint64_t*>(memb + __umulhi((uint32_t)(y) & 0x7f800u, (uint32_t)(8 * T) << 21)))
-    uint64_t xn = MEM(0);
-    uint64_t pn = MEMX(xn);
-#define ISAAC_STEP(mixexpr, i, i2, SINK)                             \
-    {                                                               \
-        const uint64_t x = xn, p = pn;                              \
-        xn = MEM(((i) + 1) & 255);  /* i == 255: a dummy load */    \
-        const uint32_t jn = ((uint32_t)xn >> 3) & 255u;             \
-        pn = MEMX(xn);                                              \
-        aa = (mixexpr) + MEM(i2);                                   \
-        const uint64_t y = p + aa + bb;                             \
-        MEM(i) = y;                                                 \
-        if (jn == (uint32_t)(i)) pn = y;                            \
-        bb = MEMY(y) + x;                                           \
-        SINK(i, bb);                                                \
+    static_assert(KEEP >= 8 && KEEP % 4 == 0 && KEEP <= 120, "KEEP");
+    constexpr int ROW = 8 * T;  // bytes between mem[i] and mem[i + 1]
+    const uint32_t col = (uint32_t)__cvta_generic_to_shared(mem);
+    // byte address of mem[(x >> 3) & 255] is col + (x & 0x7f8) * T, that of mem[(y >> 11) & 255] the high word of
+    // (y & 0x7f800) * (ROW << 21) + (col << 32); the addend is opaque so that ptxas keeps the register pair alive
+    uint64_t cbase = (uint64_t)col << 32;
+    asm("" : "+l"(cbase));
+#define ADDRX(x) (col + ((uint32_t)(x) & 0x7f8u) * (uint32_t)T)
+#define ADDRY(y) ((uint32_t)(((uint64_t)((uint32_t)(y) & 0x7f800u) * (uint64_t)((uint32_t)ROW << 21) + cbase) >> 32))
+    // Software pipeline.  At the top of step i everything y_i needs except the two data-dependent loads is in registers:
+    //   s = aa_i + x_(i-1), ax1 = address of mem[ind(x_(i+1))], x = x_i, x1, x2, m2 = mem[(i + 1) ^ 128].
+    // The step issues, in this order: y, store, p_(i+1), ldy_i, then the static-index fetches x_(i+3) and mem[(i+2)^128],
+    // and fills the shadow of the loads with aa_(i+1), s_(i+1) and the address for x_(i+2).
+    // isaac64() after init: a = b = 0, c = 1  ->  aa = 0, bb = 1: ldy = 1 with x_(-1) = 0.
+    uint64_t ldy = 1;
+    uint64_t x = lds64v<0>(col), x1 = lds64v<ROW>(col), x2 = lds64v<2 * ROW>(col);
+    uint64_t aa = 0xFFFFFFFFFFFFFFFFull + lds64v<128 * ROW>(col);  // aa_0 = ~(0 ^ (0 << 21)) + mem[128]
+    uint64_t m2 = lds64v<129 * ROW>(col);
+    uint64_t p = lds64v<0>(ADDRX(x));
+    uint32_t ax1 = ADDRX(x1);
+    uint64_t s = aa;
+    uint64_t xs = 0;  // x of the previous step: rsl[i - 1] = ldy + xs is handed out one step late, when ldy has arrived
+    // D = i - base, DX = min(i + 3, 255) - base, DM = ((i + 2) ^ 128) - base, mixexpr = the mix of step i + 1
+#define ISAAC_STEP(mixexpr, row, base, D, DX, DM, SINK)                                    \
+    {                                                                                     \
+        const uint64_t y = p + ldy + s;                                                   \
+        SINK((base) + (D) - 1, ldy + xs);                                                 \
+        const uint32_t ay = ADDRY(y);                                                     \
+        sts64v<(D) * ROW>(row, y);                                                        \
+        p = lds64v<0>(ax1);                                                               \
+        ldy = lds64v<0>(ay);                                                              \
+        const uint64_t x3 = lds64v<(DX) * ROW>(row);                                      \
+        const uint64_t m2n = lds64v<(DM) * ROW>(row);                                     \
+        aa = (mixexpr) + m2;                                                              \
+        s = aa + x;                                                                       \
+        asm("" : "+l"(s)); /* y stays ONE three-input addition behind the loads */        \
+        ax1 = ADDRX(x2);                                                                  \
+        xs = x; x = x1; x1 = x2; x2 = x3; m2 = m2n;                                       \
     }
+#define ISAAC_4STEPS(row, base, HALF, SINK)                                                                 \
+    ISAAC_STEP(aa ^ (aa >> 5), row, base, 0, 3, 2 + (HALF), SINK)                                           \
+    ISAAC_STEP(aa ^ (aa << 12), row, base, 1, 4, 3 + (HALF), SINK)                                          \
+    ISAAC_STEP(aa ^ (aa >> 33), row, base, 2, 5, 4 + (HALF), SINK)                                          \
+    ISAAC_STEP(~(aa ^ (aa << 21)), row, base, 3, 6, 5 + (HALF), SINK)
 #define ISAAC_NOSINK(i, v)
     // only the last KEEP outputs (rsl[256-KEEP .. 255], the first KEEP words of the stream) are handed to `sink`
+#define ISAAC_SINK(i, v) if ((i) >= 256 - KEEP) sink(i, v)
+    uint32_t row = col;
 #pragma unroll 1
-    for (int base = 0; base < 128; base += 4) {
-        ISAAC_STEP(~(aa ^ (aa << 21)), base, base + 128, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base + 129, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa << 12), base + 2, base + 130, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base + 131, ISAAC_NOSINK)
-    }
+    for (int base = 0; base < 124; base += 4, row += 4 * ROW) { ISAAC_4STEPS(row, base, 128, ISAAC_NOSINK) }
+    // steps 124..127: (i + 2) ^ 128 wraps to mem[0], mem[1]
+    ISAAC_STEP(aa ^ (aa >> 5), row, 124, 0, 3, 130, ISAAC_NOSINK)
+    ISAAC_STEP(aa ^ (aa << 12), row, 124, 1, 4, 131, ISAAC_NOSINK)
+    ISAAC_STEP(aa ^ (aa >> 33), row, 124, 2, 5, -124, ISAAC_NOSINK)
+    ISAAC_STEP(~(aa ^ (aa << 21)), row, 124, 3, 6, -123, ISAAC_NOSINK)
+    row += 4 * ROW;
 #pragma unroll 1
-    for (int base = 128; base < 256 - KEEP; base += 4) {
-        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126, ISAAC_NOSINK)
-        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125, ISAAC_NOSINK)
-    }
+    for (int base = 128; base < 256 - KEEP; base += 4, row += 4 * ROW) { ISAAC_4STEPS(row, base, -128, ISAAC_NOSINK) }
 #pragma unroll 1
-    for (int base = 256 - KEEP; base < 256; base += 4) {
-        ISAAC_STEP(~(aa ^ (aa << 21)), base, base - 128, sink)
-        ISAAC_STEP(aa ^ (aa >> 5), base + 1, base - 127, sink)
-        ISAAC_STEP(aa ^ (aa << 12), base + 2, base - 126, sink)
-        ISAAC_STEP(aa ^ (aa >> 33), base + 3, base - 125, sink)
-    }
+    for (int base = 256 - KEEP; base < 252; base += 4, row += 4 * ROW) { ISAAC_4STEPS(row, base, -128, ISAAC_SINK) }
+    // steps 252..255: nothing is left to prefetch (dummy loads of valid words)
+    ISAAC_STEP(aa ^ (aa >> 5), row, 252, 0, 3, -126, ISAAC_SINK)
+    ISAAC_STEP(aa ^ (aa << 12), row, 252, 1, 3, -125, ISAAC_SINK)
+    ISAAC_STEP(aa ^ (aa >> 33), row, 252, 2, 3, -125, ISAAC_SINK)
+    ISAAC_STEP(~(aa ^ (aa << 21)), row, 252, 3, 3, -125, ISAAC_SINK)
+    sink(255, ldy + xs);
+#undef ISAAC_SINK
 #undef ISAAC_NOSINK
+#undef ISAAC_4STEPS
 #undef ISAAC_STEP
-#undef MEMX
-#undef MEMY
-#undef MEM
+#undef ADDRX
+#undef ADDRY
+}
+template <int T, int KEEP, typename Sink>
+__device__ __forceinline__ void isaac64_seed(uint64_t* mem, uint64_t s0, uint64_t s1, uint64_t s2, uint64_t s3, Sink sink) {
+    isaac64_init<T>(mem, s0, s1, s2, s3);
+    isaac64_round<T, KEEP>(mem, sink);
+}
+
+// ------------------------------------------------------------------------------------ ISAAC-64, TMEM-pipelined
+// The seeding of one path is init (64 mixes: a sequential, ALU-bound chain that touches mem[] only in order) followed by
+// one round (256 steps, each waiting for a data-dependent shared-memory load).  Shared memory holds 112 states, i.e. one
+// warp per scheduler, and a single warp cannot overlap its own two phases.  Blackwell's tensor memory is a second 256 KB
+// of on-chip storage per SM -- 128 lanes x 512 columns x 32 bit = exactly one 2 KB state per lane -- that tcgen05.st / .ld
+// address with a warp-uniform column, which is all init needs.  So the CTA runs TWO warps per scheduler:
+//   producer warp (4 + w): init of path k+1 with mem[] in its TMEM lanes (pass 1 stores, pass 2 loads and stores in
+//                          place), then -- once the consumer is done with path k -- copies the state to shared memory;
+//   consumer warp (w):     the round of path k in shared memory, the kept outputs, the lens sample and the camera ray.
+// The pair meets at two named barriers per path.  The hardware interleaves the ALU-bound chain of one warp with the
+// load-latency-bound chain of the other; the per-path time drops from init + round to about max(init + copy, round).
+#ifndef HNM_TM_DIAG
+#define HNM_TM_DIAG 0  /* timing diagnostics (wrong results): 1 no round, 2 no init and no copy, 3 no copy */
+#endif
+constexpr int ISAAC_TM_LANES = 28;                       // active consumer lanes per warp: 4 x 28 = 112 columns
+constexpr int ISAAC_TM_THREADS = 256;
+static_assert(ISAAC_PATHS == 4 * ISAAC_TM_LANES, "the TMEM pipeline is laid out for 4 consumer warps x 28 lanes");
+
+HNM_D void tm_st16(uint32_t taddr, uint64_t a, uint64_t b, uint64_t c, uint64_t d, uint64_t e, uint64_t f, uint64_t g, uint64_t h) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr),
+                    "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)),
+                    "r"((uint32_t)c), "r"((uint32_t)(c >> 32)), "r"((uint32_t)d), "r"((uint32_t)(d >> 32)),
+                    "r"((uint32_t)e), "r"((uint32_t)(e >> 32)), "r"((uint32_t)f), "r"((uint32_t)(f >> 32)),
+                    "r"((uint32_t)g), "r"((uint32_t)(g >> 32)), "r"((uint32_t)h), "r"((uint32_t)(h >> 32))
+                 : "memory");
+}
+HNM_D void tm_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+HNM_D void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+HNM_D void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+HNM_D void named_barrier(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
+HNM_D uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// K paths per column: seed(k, s0..s3) is called by the producer lanes, sink(k, i, v) / done(k) by the consumer lanes
+// (`done` runs while the state of path k+1 is copied in).  Every thread of the 256-thread CTA must call this.
+template <int KEEP, typename SeedFn, typename SinkFn, typename DoneFn>
+__device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K, SeedFn seed, SinkFn sink, DoneFn done) {
+    constexpr int T = ISAAC_PATHS;
+    __shared__ uint32_t s_tmem_base;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pair = warp & 3u;
+    const uint32_t bar_free = 1 + 2 * pair, bar_ready = 2 + 2 * pair;  // named barriers of the pair (64 threads)
+    uint64_t* const mem = smem + pair * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
+#ifndef HNM_TM_CONSUMER_HI
+#define HNM_TM_CONSUMER_HI 0  /* which warps are the consumers: 0 = warps 0-3, 1 = warps 4-7 (issue-arbiter experiment) */
+#endif
+    const bool consumer = HNM_TM_CONSUMER_HI ? warp >= 4 : warp < 4;
+    const uint32_t alloc_warp = HNM_TM_CONSUMER_HI ? 0u : 4u;
+    if (consumer) {
+        // ---------------- consumer: rounds in shared memory
+        if (lane >= (uint32_t)ISAAC_TM_LANES) return;  // (a warp's barrier arrival does not depend on its exited lanes)
+        constexpr unsigned CMASK = (1u << ISAAC_TM_LANES) - 1u;
+        for (uint32_t k = 0; k < K; k++) {
+            __syncwarp(CMASK);
+            named_barrier(bar_free, 64);   // this column is free: the producer may copy the state of path k in
+            if (k > 0) done(k - 1);
+            __syncwarp(CMASK);
+            named_barrier(bar_ready, 64);  // the state of path k is in shared memory
+#if HNM_TM_DIAG != 1
+            isaac64_round<T, KEEP>(mem, [&](int i, uint64_t v) { sink(k, i, v); });
+#endif
+        }
+        if (K > 0) done(K - 1);
+        return;
+    }
+    // ---------------- producer: init in tensor memory (all 32 lanes execute the tcgen05 instructions; lanes 28-31 idle along)
+    if (warp == alloc_warp) {
+        uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_tmem_base);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    named_barrier(15, 128);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tbase = s_tmem_base + ((pair * 32u) << 16);  // lanes 32 * (warp % 4) .. + 31 belong to this warp
+    const bool active = lane < (uint32_t)ISAAC_TM_LANES;
+    for (uint32_t k = 0; k < K; k++) {
+        uint32_t m[16];
+#if HNM_TM_DIAG != 2
+        uint64_t s0, s1, s2, s3;
+        seed(k, s0, s1, s2, s3);
+        uint64_t a, b, c, d, e, f, g, h;
+        a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
+#pragma unroll
+        for (int i = 0; i < 4; i++) { ISAAC_MIX(a, b, c, d, e, f, g, h) }
+        a += s0; b += s1; c += s2; d += s3;
+#pragma unroll 1
+        for (uint32_t col = 0; col < 512; col += 16) {
+            ISAAC_MIX(a, b, c, d, e, f, g, h)
+            tm_st16(tbase + col, a, b, c, d, e, f, g, h);
+        }
+        tm_wait_st();
+        tm_ld16(tbase, m);
+#pragma unroll 1
+        for (uint32_t col = 0; col < 512; col += 16) {
+            tm_wait_ld();
+            a += u64_of(m[0], m[1]); b += u64_of(m[2], m[3]); c += u64_of(m[4], m[5]); d += u64_of(m[6], m[7]);
+            e += u64_of(m[8], m[9]); f += u64_of(m[10], m[11]); g += u64_of(m[12], m[13]); h += u64_of(m[14], m[15]);
+            tm_ld16(tbase + ((col + 16) & 511u), m);  // next block (the last iteration re-reads block 0: unused)
+            ISAAC_MIX(a, b, c, d, e, f, g, h)
+            tm_st16(tbase + col, a, b, c, d, e, f, g, h);
+        }
+        tm_wait_ld();
+        tm_wait_st();
+#endif
+        named_barrier(bar_free, 64);
+#if HNM_TM_DIAG != 2 && HNM_TM_DIAG != 3
+        // copy the finished state into the consumer's column
+        tm_ld16(tbase, m);
+#pragma unroll 1
+        for (uint32_t col = 0; col < 512; col += 16) {
+            tm_wait_ld();
+            uint64_t w0 = u64_of(m[0], m[1]), w1 = u64_of(m[2], m[3]), w2 = u64_of(m[4], m[5]), w3 = u64_of(m[6], m[7]);
+            uint64_t w4 = u64_of(m[8], m[9]), w5 = u64_of(m[10], m[11]), w6 = u64_of(m[12], m[13]), w7 = u64_of(m[14], m[15]);
+            tm_ld16(tbase + ((col + 16) & 511u), m);
+            if (active) {
+                uint64_t* o = mem + (size_t)(col >> 1) * T;
+                o[0] = w0; o[T] = w1; o[2 * T] = w2; o[3 * T] = w3; o[4 * T] = w4; o[5 * T] = w5; o[6 * T] = w6; o[7 * T] = w7;
+            }
+        }
+        tm_wait_ld();
+#endif
+        named_barrier(bar_ready, 64);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    named_barrier(15, 128);
+    if (warp == alloc_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512u) : "memory");
 }
 
 // Complete generator with refill, state in local memory: the exact slow path.
@@ -345,6 +534,65 @@ __global__ void __launch_bounds__(ISAAC_THREADS, HNM_ISAAC_MIN_BLOCKS) k_isaac_r
         store_ray(P, p, o, d, splat(1.0), p);
         P.cursor[p] = (uint8_t)cur;
     }
+}
+
+// The same generation with the TMEM pipeline above (default; HNM_ISAAC_TMEM=0 selects k_isaac_raygen for the A/B).
+#ifndef HNM_ISAAC_TM_MIN_BLOCKS
+#define HNM_ISAAC_TM_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(ISAAC_TM_THREADS, HNM_ISAAC_TM_MIN_BLOCKS) k_isaac_raygen_tm(RParams P) {
+    extern __shared__ uint64_t smem_isaac[];
+    const uint32_t N = P.N, cap = P.cap;
+    const uint32_t stride = gridDim.x * ISAAC_PATHS;
+    const uint32_t first = blockIdx.x * ISAAC_PATHS;
+    if (first >= N) return;
+    const uint32_t K = (N - first + stride - 1) / stride;  // the same count for every thread of the CTA
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t col = ((threadIdx.x >> 5) & 3u) * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
+    if (threadIdx.x < 128) note_warp_slot(P.dbg, 0);
+    auto path_of = [&](uint32_t k) { return first + k * stride + col; };
+    isaac64_tmem_pipeline<RNG_TAIL>(
+        smem_isaac, K,
+        [&](uint32_t k, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
+            uint32_t p = path_of(k);
+            p = p < N ? p : N - 1;  // a column past the end idles along on the last path
+            PathCoord c = path_coord(P, p);
+            path_seed(c, P.sampling_first + c.pass, s0, s1, s2, s3);
+        },
+        [&](uint32_t k, int i, uint64_t v) {
+            // outputs are consumed from rsl[255] downwards: word j of the stream = rsl[255 - j]
+            const uint32_t p = path_of(k);
+            if (p < N) P.tail[(size_t)(255 - i) * cap + p] = v;
+        },
+        [&](uint32_t k) {
+            const uint32_t p = path_of(k);
+            if (p >= N) return;
+            PathCoord c = path_coord(P, p);
+            const uint64_t* tail = P.tail + p;
+            // sample_on_lens (src/camera.rs:66-81): rejection loop over pairs of the stream
+            int cur = 0;
+            double sqx = 0.0, sqy = 0.0;
+            bool ok = false;
+            while (cur + 2 <= P.tail_k) {
+                double u = u64_to_f64(tail[(size_t)cur * cap]);
+                double v = u64_to_f64(tail[(size_t)(cur + 1) * cap]);
+                cur += 2;
+                sqx = 2.0 * u - 1.0;
+                sqy = 2.0 * v - 1.0;
+                if (P.cam.lens_shape == 0 || sqx * sqx + sqy * sqy < 1.0) { ok = true; break; }
+            }
+            P.L[0][p] = 0.0; P.L[1][p] = 0.0; P.L[2][p] = 0.0;
+            if (!ok || cur + 2 * (int)(P.sc.bounce_limit - 1) > P.tail_k) {
+                // the stored tail is too short for this path: exact slow path (k_rng_overflow fills the slot)
+                uint32_t slot = atomicAdd(P.ovf_counter, 1u);
+                P.q_ovf[slot] = p;
+                return;
+            }
+            D3 o, d;
+            lens_ray(P.cam, c.ncx, c.ncy, sqx, sqy, o, d);
+            store_ray(P, p, o, d, splat(1.0), p);
+            P.cursor[p] = (uint8_t)cur;
+        });
 }
 
 // First kernel of a path-tracing batch on the renderer's stream.  The generation kernels above may have run
@@ -857,6 +1105,27 @@ __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_batch(const uint64_t
             if (j < (int)count) o[j] = v;
         });
     }
+}
+__global__ void __launch_bounds__(ISAAC_TM_THREADS, 1) k_isaac_batch_tm(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
+    extern __shared__ uint64_t smem_isaac[];
+    const uint32_t stride = gridDim.x * ISAAC_PATHS, first = blockIdx.x * ISAAC_PATHS;
+    if (first >= n) return;
+    const uint32_t K = (n - first + stride - 1) / stride;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t col = ((threadIdx.x >> 5) & 3u) * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
+    isaac64_tmem_pipeline<RNG_TAIL>(
+        smem_isaac, K,
+        [&](uint32_t k, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
+            uint32_t p = first + k * stride + col;
+            p = p < n ? p : n - 1;
+            s0 = seeds[4 * p]; s1 = seeds[4 * p + 1]; s2 = seeds[4 * p + 2]; s3 = seeds[4 * p + 3];
+        },
+        [&](uint32_t k, int i, uint64_t v) {
+            const uint32_t p = first + k * stride + col;
+            const int j = 255 - i;
+            if (p < n && j < (int)count) out[(size_t)p * count + j] = v;
+        },
+        [&](uint32_t) {});
 }
 __global__ void k_isaac_full_batch(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {

@@ -106,6 +106,20 @@ d=json.loads(sys.stdin.read()); print('$prec config $c', round(d['value'],1), 'm
                  for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 6 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/young.log 2>&1; cat $OUT/young.log ;;
+    tm1)     { timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "isaac or config1 or rng" 2>&1 | tail -5
+               bash tools/ab.sh "HNM_ISAAC_TMEM=0" "HNM_ISAAC_TMEM=1" "HNM_ISAAC_TMEM=1 HNM_RNG_OVERLAP=0" "HNM_ISAAC_TMEM=1 HNM_TRACE_BLOCKS=6" "HNM_ISAAC_TMEM=1 HNM_TRACE_BLOCKS=7"; } > $OUT/tm1.log 2>&1; cat $OUT/tm1.log ;;
+    tm2)     { for v in tmdiag1 tmdiag2 tmdiag3; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done
+               HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen -c 1 -f -o gpurun_out/prof_isaactm python tools/traffic_probe.py rtcamp6 1920 1080 2>&1 | tail -2; } > $OUT/tm2.log 2>&1; cat $OUT/tm2.log ;;
+    tm3)     { timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "isaac or config1 or rng" 2>&1 | tail -3
+               for v in tmdiag2 tmnoopq; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done
+               bash tools/ab.sh "HNM_ISAAC_TMEM=0 HNM_RNG_OVERLAP=0" "HNM_ISAAC_TMEM=1 HNM_RNG_OVERLAP=0" "HNM_ISAAC_TMEM=0" "HNM_ISAAC_TMEM=1" "HNM_ISAAC_TMEM=1 HNM_TRACE_BLOCKS=6"; } > $OUT/tm3.log 2>&1; cat $OUT/tm3.log ;;
+    tm4)     { HNM_CORE_LIB=_variants/tmdiag2.so HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen -c 1 -f -o gpurun_out/prof_isaactm_d2 python tools/traffic_probe.py rtcamp6 1920 1080 2>&1 | tail -2; } > $OUT/tm4.log 2>&1; cat $OUT/tm4.log ;;
+    tm5)     { for e in "HNM_ISAAC_TMEM=0" "HNM_ISAAC_TMEM=1" "HNM_ISAAC_TMEM=1 HNM_RNG_OVERLAP=0" "HNM_ISAAC_TMEM=1 HNM_RNG_START_BOUNCE=0" "HNM_ISAAC_TMEM=1 HNM_RNG_START_BOUNCE=2" "HNM_ISAAC_TMEM=1 HNM_TRACE_BLOCKS=6"; do
+                 echo "== $e"
+                 for c in 2 4 3; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/tm5.log 2>&1; cat $OUT/tm5.log ;;
+    tm6)     { for v in tmhi; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done; } > $OUT/tm6.log 2>&1; cat $OUT/tm6.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
