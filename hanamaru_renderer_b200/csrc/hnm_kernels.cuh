@@ -319,10 +319,44 @@ HNM_D void tm_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr)
                  : "memory");
 }
+HNM_D void tm_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr)
+                 : "memory");
+}
 HNM_D void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 HNM_D void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 HNM_D void named_barrier(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory"); }
 HNM_D uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64_t)hi << 32); }
+
+// TMEM columns [c0, c1) of this warp's lanes -> words [c0 / 2, c1 / 2) of shared-memory column `mem` (stride T words).  Loads of
+// 32 columns, the next one in flight while the 16 words of the current one are stored (with one x16 load at a time the
+// loop was bound by the TMEM load latency: 0.93 -> 0.5 ms of the 7 ms kernel).  All 32 lanes must call.
+template <int T>
+HNM_D void tm_copy_to_column(uint32_t tbase, uint64_t* mem, bool active, uint32_t c0, uint32_t c1) {
+    if (c0 >= c1) return;
+    uint32_t c[32];
+    tm_ld32(tbase + c0, c);
+#pragma unroll 1
+    for (uint32_t col = c0; col < c1; col += 32) {
+        tm_wait_ld();
+        uint64_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) w[j] = u64_of(c[2 * j], c[2 * j + 1]);
+        tm_ld32(tbase + (col + 32 < c1 ? col + 32 : c0), c);  // (the last iteration re-reads the first block: unused)
+        if (active) {
+            uint64_t* o = mem + (size_t)(col >> 1) * T;
+#pragma unroll
+            for (int j = 0; j < 16; j++) o[j * T] = w[j];
+        }
+    }
+    tm_wait_ld();
+}
 
 // K paths per column: seed(k, s0..s3) is called by the producer lanes, sink(k, i, v) / done(k) by the consumer lanes
 // (`done` runs while the state of path k+1 is copied in).  Every thread of the 256-thread CTA must call this.
@@ -346,7 +380,9 @@ __device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K
         for (uint32_t k = 0; k < K; k++) {
             __syncwarp(CMASK);
             named_barrier(bar_free, 64);   // this column is free: the producer may copy the state of path k in
+#if HNM_TM_DIAG != 4
             if (k > 0) done(k - 1);
+#endif
             __syncwarp(CMASK);
             named_barrier(bar_ready, 64);  // the state of path k is in shared memory
 #if HNM_TM_DIAG != 1
@@ -366,6 +402,12 @@ __device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K
     named_barrier(15, 128);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = s_tmem_base + ((pair * 32u) << 16);  // lanes 32 * (warp % 4) .. + 31 belong to this warp
+#ifdef HNM_TM_STAGGER
+    {   // experiment: start the four pairs a quarter of an iteration apart
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)pair * HNM_TM_STAGGER) {}
+    }
+#endif
     const bool active = lane < (uint32_t)ISAAC_TM_LANES;
     for (uint32_t k = 0; k < K; k++) {
         uint32_t m[16];
@@ -398,25 +440,14 @@ __device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K
 #endif
         named_barrier(bar_free, 64);
 #if HNM_TM_DIAG != 2 && HNM_TM_DIAG != 3
-        // copy the finished state into the consumer's column
-        tm_ld16(tbase, m);
-#pragma unroll 1
-        for (uint32_t col = 0; col < 512; col += 16) {
-            tm_wait_ld();
-            uint64_t w0 = u64_of(m[0], m[1]), w1 = u64_of(m[2], m[3]), w2 = u64_of(m[4], m[5]), w3 = u64_of(m[6], m[7]);
-            uint64_t w4 = u64_of(m[8], m[9]), w5 = u64_of(m[10], m[11]), w6 = u64_of(m[12], m[13]), w7 = u64_of(m[14], m[15]);
-            tm_ld16(tbase + ((col + 16) & 511u), m);
-            if (active) {
-                uint64_t* o = mem + (size_t)(col >> 1) * T;
-                o[0] = w0; o[T] = w1; o[2 * T] = w2; o[3 * T] = w3; o[4 * T] = w4; o[5 * T] = w5; o[6 * T] = w6; o[7 * T] = w7;
-            }
-        }
-        tm_wait_ld();
+        // copy the finished state into the consumer's column.  (Letting the consumer warp copy a share itself -- its lanes
+        // 28-31 kept alive for the warp-wide tcgen05.ld -- was measured slower for every split: 6.56 -> 8.1-8.6 ms.)
+        tm_copy_to_column<T>(tbase, mem, active, 0, 512);
 #endif
         named_barrier(bar_ready, 64);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    named_barrier(15, 128);
+    named_barrier(14, 128);  // the producers only (no other warp touches tensor memory)
     if (warp == alloc_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512u) : "memory");
 }
 

@@ -120,6 +120,10 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/tm5.log 2>&1; cat $OUT/tm5.log ;;
     tm6)     { for v in tmhi; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done; } > $OUT/tm6.log 2>&1; cat $OUT/tm6.log ;;
+    tm7)     { for v in tmdiag3 tmdiag4 tmstag; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done; } > $OUT/tm7.log 2>&1; cat $OUT/tm7.log ;;
+    tm8)     { timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; bash tools/ab.sh "HNM_RNG_OVERLAP=0" "HNM_X=1"; } > $OUT/tm8.log 2>&1; cat $OUT/tm8.log ;;
+    tm9)     { timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60
+               for v in tmcs0 tmcs64 tmcs256; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done; } > $OUT/tm9.log 2>&1; cat $OUT/tm9.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
