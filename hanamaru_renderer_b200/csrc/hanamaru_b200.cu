@@ -78,6 +78,7 @@ struct hnm_renderer {
         double* ray[6] = {}; double* thr[3] = {}; uint32_t* pid = nullptr;
         double* L[3] = {}; uint8_t* cursor = nullptr; uint64_t* tail = nullptr;
         uint32_t* q_ovf = nullptr; uint32_t* ovf_counter = nullptr;
+        uint32_t* gen_next = nullptr;  // sliced generation: next path k_isaac_raygen_tm hands out
         cudaEvent_t ready = nullptr, released = nullptr;
         bool valid = false;        // holds the generated batch (sampling_first, batch), not consumed yet
         bool ready_recorded = false, released_recorded = false;
@@ -89,6 +90,13 @@ struct hnm_renderer {
     bool speculate = true;         // HNM_RNG_SPECULATE=0: no prefetch across hnm_render_passes calls
     int rng_start_bounce = 1;      // HNM_RNG_START_BOUNCE=k: the prefetch is released after bounce k of the current batch (measured best of 0..4)
     cudaEvent_t rng_gate = nullptr;
+    // Sliced generation (HNM_RNG_SLICES=k, default 4; 0 = one launch released after bounce HNM_RNG_START_BOUNCE): the generation of the next batch runs as k stoppable launches of
+    // k_isaac_raygen_tm, one beside the confirm / shade kernels of each of the first k bounces -- never beside k_trace,
+    // which competes with it for the same issue slots and integer pipe -- and one last launch that finishes the set.
+    int rng_slices = 4;
+    uint32_t* gen_stop = nullptr;    // device word: stop level (k_gen_stop raises it, a slice of level <= it winds down)
+    uint32_t gen_epoch = 0;          // level of the last stoppable slice
+    cudaEvent_t slice_open[8] = {}, slice_done[8] = {};
     uint64_t gen_wasted = 0;       // speculative generations that were never consumed
     int sm_count = 148;
     CandLists cand = {};           // candidate lists of the rays in flight: camera rays [0, cap), shadow rays [cap, cap + scap)
@@ -171,8 +179,9 @@ void bind_gen_set(RParams& P, const hnm_renderer::GenSet& g) {
     P.cursor = g.cursor; P.tail = g.tail; P.q_ovf = g.q_ovf; P.ovf_counter = g.ovf_counter;
 }
 
-// ISAAC seeding + lens sampling + first-bounce rays of batch (sampling_first, batch) into set `g`, on stream `on`
-int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, uint32_t batch, cudaStream_t on) {
+// ISAAC seeding + lens sampling + first-bounce rays of batch (sampling_first, batch) into set `g`, on stream `on`:
+// generate_begin, any number of generate_slice launches (each carries on where the previous one stopped), generate_finish.
+RParams gen_params(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, uint32_t batch) {
     RParams G = r->P;
     G.batch = batch;
     G.sampling_first = sampling_first;
@@ -181,22 +190,45 @@ int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, 
     for (int k = 0; k < 6; k++) G.rout[k] = g.ray[k];
     for (int k = 0; k < 3; k++) G.tout[k] = g.thr[k];
     G.pout = g.pid;
+    G.gen_next = g.gen_next;
+    G.gen_stop = r->gen_stop;
+    G.gen_epoch = 0xFFFFFFFFu;
+    return G;
+}
+int generate_begin(hnm_renderer* r, hnm_renderer::GenSet& g, cudaStream_t on) {
     HNM_CUDA(cudaMemsetAsync(g.ovf_counter, 0, sizeof(uint32_t), on));
-    size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
-    // Grid: one persistent CTA per SM, or (isaac_rounds > 0) short-lived CTAs of `isaac_rounds` x 112 paths.  The SM's issue
-    // arbiter serves the OLDEST resident warps first (tools/microbench/prio.cu): a persistent generation CTA outranks every
-    // kernel launched after it, short-lived ones are younger than the persistent k_trace CTAs they run next to.
-    int igrid = r->sm_count;
-    if (r->isaac_rounds > 0 && on == r->rng_stream)
-        igrid = (int)std::max<uint64_t>(r->sm_count, ((uint64_t)G.N + (uint64_t)ISAAC_PATHS * r->isaac_rounds - 1) / ((uint64_t)ISAAC_PATHS * r->isaac_rounds));
-    if (r->isaac_tmem)
-        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen_tm<<<r->sm_count, ISAAC_TM_THREADS, smem, on>>>(G); }, on);
-    else
-        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<igrid, ISAAC_THREADS, smem, on>>>(G); }, on);
+    HNM_CUDA(cudaMemsetAsync(g.gen_next, 0, sizeof(uint32_t), on));
+    (void)r;
+    return 0;
+}
+// one launch of the generation kernel; epoch = 0xFFFFFFFF: runs until the set is complete
+void generate_slice(hnm_renderer* r, RParams& G, uint32_t epoch, cudaStream_t on) {
+    const size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
+    G.gen_epoch = epoch;
+    launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen_tm<<<r->sm_count, ISAAC_TM_THREADS, smem, on>>>(G); }, on);
+}
+void generate_finish(hnm_renderer* r, hnm_renderer::GenSet& g, RParams& G, uint32_t sampling_first, uint32_t batch, cudaStream_t on) {
     launch_timed(r, "rng_overflow", [&] { k_rng_overflow<<<r->sm_count, 64, 0, on>>>(G); }, on);
     g.valid = true;
     g.sampling_first = sampling_first;
     g.batch = batch;
+}
+int generate(hnm_renderer* r, hnm_renderer::GenSet& g, uint32_t sampling_first, uint32_t batch, cudaStream_t on) {
+    RParams G = gen_params(r, g, sampling_first, batch);
+    int rc = generate_begin(r, g, on);
+    if (rc) return rc;
+    if (r->isaac_tmem) {
+        generate_slice(r, G, 0xFFFFFFFFu, on);
+    } else {
+        const size_t smem = (size_t)ISAAC_PATHS * 256 * sizeof(uint64_t);
+        // Grid: one persistent CTA per SM, or (isaac_rounds > 0) short-lived CTAs of `isaac_rounds` x 112 paths (A/B: the SM's
+        // issue arbiter serves the oldest resident warps first, tools/microbench/prio.cu; measured slower)
+        int igrid = r->sm_count;
+        if (r->isaac_rounds > 0 && on == r->rng_stream)
+            igrid = (int)std::max<uint64_t>(r->sm_count, ((uint64_t)G.N + (uint64_t)ISAAC_PATHS * r->isaac_rounds - 1) / ((uint64_t)ISAAC_PATHS * r->isaac_rounds));
+        launch_timed(r, "isaac_raygen", [&] { k_isaac_raygen<<<igrid, ISAAC_THREADS, smem, on>>>(G); }, on);
+    }
+    generate_finish(r, g, G, sampling_first, batch, on);
     return 0;
 }
 
@@ -325,8 +357,43 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
         };
         const bool want_prefetch = overlap && next_batch > 0;
         int hook_rc = 0;
-        r->prefetch_hook = [&] { hook_rc = prefetch_next(); };
-        if (want_prefetch && r->rng_start_bounce <= 0) { int rc = prefetch_next(); if (rc) return rc; }
+        // ---- sliced prefetch: stoppable generation launches beside the confirm / shade kernels of the first bounces
+        hnm_renderer::GenSet& o = r->gen[s ^ 1];
+        const bool sliced = want_prefetch && r->isaac_tmem && r->rng_slices > 0 &&
+                            !(o.valid && o.sampling_first == next_first && o.batch == next_batch);
+        RParams G;
+        uint32_t slice_epoch = 0;
+        int slices_left = sliced ? std::min(std::min(r->rng_slices, 8), last) : 0;
+        bool gen_finished = false;
+        auto finish_generation = [&]() {
+            generate_slice(r, G, 0xFFFFFFFFu, r->rng_stream);  // whatever is left, not stoppable
+            generate_finish(r, o, G, next_first, next_batch, r->rng_stream);
+            if (cudaEventRecord(o.ready, r->rng_stream) != cudaSuccess) hook_rc = set_error(HNM_ERR_CUDA, "cudaEventRecord failed");
+            o.ready_recorded = true;
+            gen_finished = true;
+        };
+        if (sliced) {
+            if (o.valid) r->gen_wasted++;
+            o.valid = false;
+            if (o.released_recorded) HNM_CUDA(cudaStreamWaitEvent(r->rng_stream, o.released, 0));
+            G = gen_params(r, o, next_first, next_batch);
+            int rc = generate_begin(r, o, r->rng_stream);
+            if (rc) return rc;
+            r->prefetch_hook = [&] {
+                // called right behind this bounce's k_trace launch: the slice starts when the trace has finished ...
+                const int i = slices_left;
+                if (cudaEventRecord(r->slice_open[i & 7], st) != cudaSuccess || cudaStreamWaitEvent(r->rng_stream, r->slice_open[i & 7], 0) != cudaSuccess) {
+                    hook_rc = set_error(HNM_ERR_CUDA, "slice events failed");
+                    return;
+                }
+                slice_epoch = ++r->gen_epoch;
+                generate_slice(r, G, slice_epoch, r->rng_stream);
+                if (cudaEventRecord(r->slice_done[i & 7], r->rng_stream) != cudaSuccess) hook_rc = set_error(HNM_ERR_CUDA, "slice events failed");
+            };
+        } else {
+            r->prefetch_hook = [&] { hook_rc = prefetch_next(); };
+            if (want_prefetch && r->rng_start_bounce <= 0) { int rc = prefetch_next(); if (rc) return rc; }
+        }
         bind_gen_set(P, g);
         launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
         for (int b = 1; b <= last; b++) {
@@ -335,7 +402,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             TraceJob cam = camera_job(P, b, true);
             // HNM_RNG_MIDTRACE: the generation kernel is enqueued right BEHIND this bounce's trace launch with no dependency
             // on it, so that its CTAs are placed while the trace CTAs are already resident (issue arbitration)
-            const bool mid = want_prefetch && r->rng_midtrace && b == r->rng_start_bounce;
+            const bool slice_here = sliced && slices_left > 0;
+            const bool mid = slice_here || (!sliced && want_prefetch && r->rng_midtrace && b == r->rng_start_bounce);
             if (b > 1) {
                 TraceJob sh = shadow_job(P, b - 1);
                 launch_trace(r, trace_name(r, b), &cam, &sh, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS, true, mid);
@@ -352,7 +420,15 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
                 launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<grid, 256, 0, st>>>(P, b); });
                 launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<grid, 256, 0, st>>>(P, b); });
             }
-            if (want_prefetch && !r->rng_midtrace && b == r->rng_start_bounce) {
+            if (slice_here) {
+                // ... and winds down when this bounce's shade kernels are done; the next trace waits for it
+                const int i = slices_left;
+                k_gen_stop<<<1, 1, 0, st>>>(r->gen_stop, slice_epoch);
+                HNM_CUDA(cudaStreamWaitEvent(st, r->slice_done[i & 7], 0));
+                slices_left--;
+                if (slices_left == 0) finish_generation();  // the rest runs beside the thin late bounces
+            }
+            if (!sliced && want_prefetch && !r->rng_midtrace && b == r->rng_start_bounce) {
                 // the generation of the next batch starts here: the thin late bounces leave the SMs under-used
                 HNM_CUDA(cudaEventRecord(r->rng_gate, st));
                 HNM_CUDA(cudaStreamWaitEvent(r->rng_stream, r->rng_gate, 0));
@@ -360,6 +436,7 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
                 if (rc) return rc;
             }
         }
+        if (sliced && !gen_finished) finish_generation();
         TraceJob sh = shadow_job(P, last);
         launch_trace(r, trace_name(r, last + 1), &sh, nullptr, &P.counters[(last + 1) * C_STRIDE + C_WORK], -1, false);
         launch_nee_resolve(r, last);
@@ -487,6 +564,7 @@ void hnm_renderer_destroy(hnm_renderer* r) {
         if (g.released) cudaEventDestroy(g.released);
     }
     if (r->rng_gate) cudaEventDestroy(r->rng_gate);
+    for (int k = 0; k < 8; k++) { if (r->slice_open[k]) cudaEventDestroy(r->slice_open[k]); if (r->slice_done[k]) cudaEventDestroy(r->slice_done[k]); }
     if (r->rng_stream) cudaStreamDestroy(r->rng_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
     delete r;
@@ -525,6 +603,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
     if (const char* e = getenv("HNM_ISAAC_TMEM")) r->isaac_tmem = atoi(e) != 0;
+    if (const char* e = getenv("HNM_RNG_SLICES")) r->rng_slices = std::max(0, std::min(8, atoi(e)));
     if (const char* e = getenv("HNM_ISAAC_ROUNDS")) r->isaac_rounds = std::max(0, atoi(e));
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }
     if (const char* e = getenv("HNM_RNG_OVERLAP")) r->overlap = atoi(e) != 0;
@@ -590,6 +669,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
                 A.take(&g.tail, cap * RNG_TAIL);
                 A.take(&g.q_ovf, cap);
                 A.take(&g.ovf_counter, (size_t)4);
+                A.take(&g.gen_next, (size_t)4);
             }
         }
         A.take(&P.hit_t, cap); A.take(&P.hit_u, cap); A.take(&P.hit_v, cap); A.take(&P.hit_id, cap);
@@ -606,6 +686,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         A.take(&r->cand.id, nl * TRACE_CAND); A.take(&r->cand.lo, nl * TRACE_CAND);
         A.take(&r->cand.n, nl); A.take(&r->cand.ub, nl);
         A.take(&P.counters, (size_t)NUM_COUNTERS);
+        A.take(&r->gen_stop, (size_t)4);
         A.take(&P.stats, (size_t)S_COUNT);
         A.take(&P.accum, accum_n);
         if (r->wid_stats) A.take(&P.dbg, (size_t)8);
@@ -628,9 +709,15 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
         }
     }
     if (cudaEventCreateWithFlags(&r->rng_gate, cudaEventDisableTiming) != cudaSuccess) { set_error(HNM_ERR_CUDA, "cudaEventCreate failed"); return bail(HNM_ERR_CUDA); }
+    for (int k = 0; k < 8; k++)
+        if (cudaEventCreateWithFlags(&r->slice_open[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&r->slice_done[k], cudaEventDisableTiming) != cudaSuccess) {
+            set_error(HNM_ERR_CUDA, "cudaEventCreate failed");
+            return bail(HNM_ERR_CUDA);
+        }
     bind_gen_set(P, r->gen[0]);
     ce = cudaMemsetAsync(P.accum, 0, accum_n * sizeof(double), r->stream);
     if (ce == cudaSuccess) ce = cudaMemsetAsync(P.stats, 0, S_COUNT * sizeof(unsigned long long), r->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(r->gen_stop, 0, sizeof(uint32_t), r->stream);
     if (ce == cudaSuccess && P.dbg) ce = cudaMemsetAsync(P.dbg, 0, 8 * sizeof(unsigned long long), r->stream);
     if (ce == cudaSuccess && mode == HNM_MODE_PATHTRACING)
         ce = cudaFuncSetAttribute(k_isaac_raygen, cudaFuncAttributeMaxDynamicSharedMemorySize, ISAAC_PATHS * 256 * (int)sizeof(uint64_t));

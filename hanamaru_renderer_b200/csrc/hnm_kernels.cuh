@@ -87,6 +87,8 @@ struct RParams {
     uint32_t* q_miss; uint32_t* q_delta; uint32_t* q_nee;
     // exact-slow-path list of the generation set that L / cursor / tail belong to (see GenSet, hanamaru_b200.cu)
     uint32_t* q_ovf; uint32_t* ovf_counter;
+    // sliced generation (k_isaac_raygen_tm): next path to hand out (per generation set), stop level (per renderer), this launch's level
+    uint32_t* gen_next; const uint32_t* gen_stop; uint32_t gen_epoch;
     // NEE events of the current bounce and their shadow rays (num_emissions per event, event-major)
     double* ev_thr[3]; double* ev_albedo[3]; double* ev_emission[3]; uint32_t* ev_pid;
     double* sray[6]; double* s_pos[3]; double* s_bsdf; double* s_g;
@@ -358,42 +360,45 @@ HNM_D void tm_copy_to_column(uint32_t tbase, uint64_t* mem, bool active, uint32_
     tm_wait_ld();
 }
 
-// K paths per column: seed(k, s0..s3) is called by the producer lanes, sink(k, i, v) / done(k) by the consumer lanes
-// (`done` runs while the state of path k+1 is copied in).  Every thread of the 256-thread CTA must call this.
-template <int KEEP, typename SeedFn, typename SinkFn, typename DoneFn>
-__device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K, SeedFn seed, SinkFn sink, DoneFn done) {
+// Work is handed out per warp PAIR, 28 consecutive paths at a time: fetch() is called by the producer warp (every lane gets the
+// same answer) and returns the first path of the next group or ISAAC_NONE; seed(p, s0..s3) is called by the producer lanes
+// for path p = group + lane; sink(p, i, v) and done(p) by the consumer lanes (`done` runs while the state of the next group is
+// copied in).  Every thread of the 256-thread CTA must call this.
+constexpr uint32_t ISAAC_NONE = 0xFFFFFFFFu;
+template <int KEEP, typename FetchFn, typename SeedFn, typename SinkFn, typename DoneFn>
+__device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, FetchFn fetch, SeedFn seed, SinkFn sink, DoneFn done) {
     constexpr int T = ISAAC_PATHS;
     __shared__ uint32_t s_tmem_base;
+    __shared__ uint32_t s_group[4];  // the group whose state the producer has just copied into the pair's columns
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t pair = warp & 3u;
     const uint32_t bar_free = 1 + 2 * pair, bar_ready = 2 + 2 * pair;  // named barriers of the pair (64 threads)
     uint64_t* const mem = smem + pair * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
-#ifndef HNM_TM_CONSUMER_HI
-#define HNM_TM_CONSUMER_HI 0  /* which warps are the consumers: 0 = warps 0-3, 1 = warps 4-7 (issue-arbiter experiment) */
-#endif
-    const bool consumer = HNM_TM_CONSUMER_HI ? warp >= 4 : warp < 4;
-    const uint32_t alloc_warp = HNM_TM_CONSUMER_HI ? 0u : 4u;
-    if (consumer) {
+    if (warp < 4) {
         // ---------------- consumer: rounds in shared memory
         if (lane >= (uint32_t)ISAAC_TM_LANES) return;  // (a warp's barrier arrival does not depend on its exited lanes)
         constexpr unsigned CMASK = (1u << ISAAC_TM_LANES) - 1u;
-        for (uint32_t k = 0; k < K; k++) {
+        uint32_t prev = ISAAC_NONE;
+        for (;;) {
             __syncwarp(CMASK);
-            named_barrier(bar_free, 64);   // this column is free: the producer may copy the state of path k in
+            named_barrier(bar_free, 64);   // these columns are free: the producer may copy the next state in
 #if HNM_TM_DIAG != 4
-            if (k > 0) done(k - 1);
+            if (prev != ISAAC_NONE) done(prev + lane);
 #endif
             __syncwarp(CMASK);
-            named_barrier(bar_ready, 64);  // the state of path k is in shared memory
+            named_barrier(bar_ready, 64);  // the next state is in shared memory (or there is none)
+            const uint32_t cur = *(volatile uint32_t*)&s_group[pair];
+            if (cur == ISAAC_NONE) break;
 #if HNM_TM_DIAG != 1
-            isaac64_round<T, KEEP>(mem, [&](int i, uint64_t v) { sink(k, i, v); });
+            const uint32_t path = cur + lane;
+            isaac64_round<T, KEEP>(mem, [&](int i, uint64_t v) { sink(path, i, v); });
 #endif
+            prev = cur;
         }
-        if (K > 0) done(K - 1);
         return;
     }
     // ---------------- producer: init in tensor memory (all 32 lanes execute the tcgen05 instructions; lanes 28-31 idle along)
-    if (warp == alloc_warp) {
+    if (warp == 4) {
         uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_tmem_base);
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(dst), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -409,11 +414,18 @@ __device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K
     }
 #endif
     const bool active = lane < (uint32_t)ISAAC_TM_LANES;
-    for (uint32_t k = 0; k < K; k++) {
+    for (;;) {
+        const uint32_t group = fetch();
+        if (group == ISAAC_NONE) {
+            named_barrier(bar_free, 64);
+            if (lane == 0) *(volatile uint32_t*)&s_group[pair] = ISAAC_NONE;
+            named_barrier(bar_ready, 64);
+            break;
+        }
         uint32_t m[16];
 #if HNM_TM_DIAG != 2
         uint64_t s0, s1, s2, s3;
-        seed(k, s0, s1, s2, s3);
+        seed(group + (active ? lane : 0u), s0, s1, s2, s3);
         uint64_t a, b, c, d, e, f, g, h;
         a = b = c = d = e = f = g = h = 0x9e3779b97f4a7c13ull;
 #pragma unroll
@@ -440,15 +452,16 @@ __device__ __forceinline__ void isaac64_tmem_pipeline(uint64_t* smem, uint32_t K
 #endif
         named_barrier(bar_free, 64);
 #if HNM_TM_DIAG != 2 && HNM_TM_DIAG != 3
-        // copy the finished state into the consumer's column.  (Letting the consumer warp copy a share itself -- its lanes
+        // copy the finished state into the consumer's columns.  (Letting the consumer warp copy a share itself -- its lanes
         // 28-31 kept alive for the warp-wide tcgen05.ld -- was measured slower for every split: 6.56 -> 8.1-8.6 ms.)
         tm_copy_to_column<T>(tbase, mem, active, 0, 512);
 #endif
+        if (lane == 0) *(volatile uint32_t*)&s_group[pair] = group;
         named_barrier(bar_ready, 64);
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     named_barrier(14, 128);  // the producers only (no other warp touches tensor memory)
-    if (warp == alloc_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512u) : "memory");
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(s_tmem_base), "r"(512u) : "memory");
 }
 
 // Complete generator with refill, state in local memory: the exact slow path.
@@ -574,29 +587,34 @@ __global__ void __launch_bounds__(ISAAC_THREADS, HNM_ISAAC_MIN_BLOCKS) k_isaac_r
 __global__ void __launch_bounds__(ISAAC_TM_THREADS, HNM_ISAAC_TM_MIN_BLOCKS) k_isaac_raygen_tm(RParams P) {
     extern __shared__ uint64_t smem_isaac[];
     const uint32_t N = P.N, cap = P.cap;
-    const uint32_t stride = gridDim.x * ISAAC_PATHS;
-    const uint32_t first = blockIdx.x * ISAAC_PATHS;
-    if (first >= N) return;
-    const uint32_t K = (N - first + stride - 1) / stride;  // the same count for every thread of the CTA
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = ((threadIdx.x >> 5) & 3u) * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
     if (threadIdx.x < 128) note_warp_slot(P.dbg, 0);
-    auto path_of = [&](uint32_t k) { return first + k * stride + col; };
     isaac64_tmem_pipeline<RNG_TAIL>(
-        smem_isaac, K,
-        [&](uint32_t k, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
-            uint32_t p = path_of(k);
+        smem_isaac,
+        [&]() -> uint32_t {
+            // The next 28 paths of the generation set, from a counter that survives the launch: a launch may be told to stop
+            // (gen_stop >= gen_epoch, raised by k_gen_stop on the renderer's stream) and the next launch carries on where it
+            // left off -- hanamaru_b200.cu runs the generation in slices beside the shade kernels of every bounce.
+            uint32_t g = ISAAC_NONE;
+            if (lane == 0) {
+                const bool stop = *(volatile const uint32_t*)P.gen_stop >= P.gen_epoch;
+                if (!stop) {
+                    g = atomicAdd(P.gen_next, (uint32_t)ISAAC_TM_LANES);
+                    if (g >= N) g = ISAAC_NONE;
+                }
+            }
+            return __shfl_sync(0xFFFFFFFFu, g, 0);
+        },
+        [&](uint32_t p, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
             p = p < N ? p : N - 1;  // a column past the end idles along on the last path
             PathCoord c = path_coord(P, p);
             path_seed(c, P.sampling_first + c.pass, s0, s1, s2, s3);
         },
-        [&](uint32_t k, int i, uint64_t v) {
+        [&](uint32_t p, int i, uint64_t v) {
             // outputs are consumed from rsl[255] downwards: word j of the stream = rsl[255 - j]
-            const uint32_t p = path_of(k);
             if (p < N) P.tail[(size_t)(255 - i) * cap + p] = v;
         },
-        [&](uint32_t k) {
-            const uint32_t p = path_of(k);
+        [&](uint32_t p) {
             if (p >= N) return;
             PathCoord c = path_coord(P, p);
             const uint64_t* tail = P.tail + p;
@@ -625,6 +643,8 @@ __global__ void __launch_bounds__(ISAAC_TM_THREADS, HNM_ISAAC_TM_MIN_BLOCKS) k_i
             P.cursor[p] = (uint8_t)cur;
         });
 }
+// raises the stop level of the sliced generation (see k_isaac_raygen_tm)
+__global__ void k_gen_stop(uint32_t* gen_stop, uint32_t epoch) { atomicMax(gen_stop, epoch); }
 
 // First kernel of a path-tracing batch on the renderer's stream.  The generation kernels above may have run
 // long before (on the RNG stream, overlapped with the previous batch), so they do not touch `counters` / `stats`.
@@ -1139,20 +1159,21 @@ __global__ void __launch_bounds__(ISAAC_THREADS, 1) k_isaac_batch(const uint64_t
 }
 __global__ void __launch_bounds__(ISAAC_TM_THREADS, 1) k_isaac_batch_tm(const uint64_t* seeds, uint32_t n, uint32_t count, uint64_t* out) {
     extern __shared__ uint64_t smem_isaac[];
-    const uint32_t stride = gridDim.x * ISAAC_PATHS, first = blockIdx.x * ISAAC_PATHS;
-    if (first >= n) return;
-    const uint32_t K = (n - first + stride - 1) / stride;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t col = ((threadIdx.x >> 5) & 3u) * ISAAC_TM_LANES + (lane < (uint32_t)ISAAC_TM_LANES ? lane : 0u);
+    // static distribution: pair w of CTA b takes groups (4 b + w), (4 b + w) + 4 gridDim, ...
+    uint32_t next = (blockIdx.x * 4u + ((threadIdx.x >> 5) & 3u)) * ISAAC_TM_LANES;
+    const uint32_t stride = gridDim.x * 4u * ISAAC_TM_LANES;
     isaac64_tmem_pipeline<RNG_TAIL>(
-        smem_isaac, K,
-        [&](uint32_t k, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
-            uint32_t p = first + k * stride + col;
+        smem_isaac,
+        [&]() -> uint32_t {
+            const uint32_t g = next < n ? next : ISAAC_NONE;
+            next += stride;
+            return g;
+        },
+        [&](uint32_t p, uint64_t& s0, uint64_t& s1, uint64_t& s2, uint64_t& s3) {
             p = p < n ? p : n - 1;
             s0 = seeds[4 * p]; s1 = seeds[4 * p + 1]; s2 = seeds[4 * p + 2]; s3 = seeds[4 * p + 3];
         },
-        [&](uint32_t k, int i, uint64_t v) {
-            const uint32_t p = first + k * stride + col;
+        [&](uint32_t p, int i, uint64_t v) {
             const int j = 255 - i;
             if (p < n && j < (int)count) out[(size_t)p * count + j] = v;
         },

@@ -211,7 +211,7 @@ def test_skybox_sample_edge_cases(hr, core, oracle, get_scene, get_device_scene)
 # ---------------------------------------------------------------------------------------- run-time switches
 @pytest.mark.parametrize("env", [{"HNM_BVH": "ref"}, {"HNM_SHADOW_BOUNDED": "0"}, {"HNM_RNG_OVERLAP": "0"}, {"HNM_RNG_SPECULATE": "0"},
                                  {"HNM_RNG_START_BOUNCE": "0"}, {"HNM_RNG_START_BOUNCE": "3"}, {"HNM_TRACE_BLOCKS": "5"},
-                                 {"HNM_ISAAC_TMEM": "0"}, {"HNM_BVH": "ref", "HNM_SHADOW_BOUNDED": "0", "HNM_RNG_OVERLAP": "0"}])
+                                 {"HNM_ISAAC_TMEM": "0"}, {"HNM_RNG_SLICES": "0"}, {"HNM_RNG_SLICES": "1"}, {"HNM_BVH": "ref", "HNM_SHADOW_BOUNDED": "0", "HNM_RNG_OVERLAP": "0"}])
 def test_switches_do_not_change_bits(hr, core, oracle, get_scene, monkeypatch, env):
     """Every switch DESIGN.md names only changes HOW the same result is computed: the reference's median-split topology
     instead of the SAH tree, unbounded shadow queries, no generation/trace overlap, no speculative generation."""

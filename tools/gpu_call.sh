@@ -124,6 +124,18 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
     tm8)     { timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; bash tools/ab.sh "HNM_RNG_OVERLAP=0" "HNM_X=1"; } > $OUT/tm8.log 2>&1; cat $OUT/tm8.log ;;
     tm9)     { timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60
                for v in tmcs0 tmcs64 tmcs256; do echo "== $v"; HNM_CORE_LIB=_variants/$v.so HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60; done; } > $OUT/tm9.log 2>&1; cat $OUT/tm9.log ;;
+    tm10)    { for e in "HNM_X=1" "HNM_RNG_OVERLAP=0" "HNM_CORE_LIB=_variants/tm64.so" "HNM_CORE_LIB=_variants/tm64.so HNM_TRACE_BLOCKS=6"; do
+                 echo "== $e"
+                 for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/tm10.log 2>&1; cat $OUT/tm10.log ;;
+    sl1)     { timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "isaac or config1 or rng or batching or scenes_bit_exact" 2>&1 | tail -3
+               for e in "HNM_RNG_SLICES=0" "HNM_RNG_SLICES=1" "HNM_RNG_SLICES=2" "HNM_RNG_SLICES=3" "HNM_RNG_SLICES=5"; do
+                 echo "== $e"
+                 for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/sl1.log 2>&1; cat $OUT/sl1.log ;;
+    sl2)     { for e in "HNM_RNG_SLICES=5 HNM_PROFILE_OVERLAP=1" "HNM_RNG_SLICES=0 HNM_PROFILE_OVERLAP=1" "HNM_RNG_OVERLAP=0"; do echo "== $e"; env $e timeout 200 python tools/time_passes.py rtcamp6 1920 1080 12 2>&1 | tail -2; done; } > $OUT/sl2.log 2>&1; cat $OUT/sl2.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
