@@ -253,8 +253,12 @@ def run_ours(args):
     tile_rows = int(os.environ.get("HNM_TILE_ROWS", hd.DEFAULT_TILE_ROWS))
     shard = (rank, world, tile_rows) if use_dist else None
     ctx = hr.RenderContext(dev, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
+    comm = None
     if use_dist:
-        ctx.dist_init(share_unique_id(), rank, world)
+        # ONE communicator per process (hnm_comm_create), made right after the launcher's rendezvous like the process group
+        # itself; every renderer of the process attaches to it.  (ncclCommInitRank takes 2-3 s at 8 ranks.)
+        comm = hr.DistComm(local, share_unique_id(), rank, world)
+        ctx.dist_attach(comm)
     if args.precision == "fast":
         ctx.set_precision(1)   # opt-in perf mode: NOT the parity path, reported only when asked for
     P = args.pps or cfg["pps"]
@@ -358,7 +362,6 @@ def run_ours(args):
     ctx = None
     e2e = None
     if not args.no_e2e:
-        uid = share_unique_id() if use_dist else None   # side channel, outside the timed region like the launcher's rendezvous
         barrier()
         imgbuf = np.zeros((HEIGHT, WIDTH, 3), np.uint8)
         scene_bytes = scene_host_bytes(scene)
@@ -366,7 +369,7 @@ def run_ours(args):
         dev2 = hr.DeviceScene(scene, local)                       # H2D: the flat scene description (host arrays)
         ctx2 = hr.RenderContext(dev2, scene.camera, WIDTH, HEIGHT, hr.MODE_PATHTRACING, shard=shard, max_batch=args.batch)
         if use_dist:
-            ctx2.dist_init(uid, rank, world)
+            ctx2.dist_attach(comm)
         if args.precision == "fast":
             ctx2.set_precision(1)
         for i in range(K):

@@ -356,6 +356,11 @@ class RenderContext:
         buf = (C.c_uint8 * _ffi.HNM_DIST_ID_BYTES).from_buffer_copy(bytes(unique_id))
         _check(_ffi.core().hnm_dist_init(self._h, buf, rank, num_ranks))
 
+    def dist_attach(self, comm):
+        """Use a process-lifetime communicator (DistComm) instead of creating one for this renderer."""
+        _check(_ffi.core().hnm_dist_attach(self._h, comm._h))
+        self._comm = comm  # keep it alive
+
     def dist_resolve(self, sampling, out=None, want_image=True):
         """Collective.  Ranks with want_image=False only take part in the gather (asynchronously) and return None."""
         if not want_image:
@@ -380,6 +385,28 @@ def dist_unique_id():
     buf = (C.c_uint8 * _ffi.HNM_DIST_ID_BYTES)()
     _check(_ffi.core().hnm_dist_unique_id(buf))
     return bytes(buf)
+
+
+class DistComm:
+    """hnm_comm: one NCCL communicator per process, created after the launcher's rendezvous and attached to every
+    renderer the process makes (ncclCommInitRank takes seconds at 8 ranks; a renderer lives for one `render` call)."""
+
+    def __init__(self, device, unique_id, rank, num_ranks):
+        buf = (C.c_uint8 * _ffi.HNM_DIST_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        h = C.c_void_p()
+        _check(_ffi.core().hnm_comm_create(device, buf, rank, num_ranks, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            _ffi.core().hnm_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class RenderGroup:

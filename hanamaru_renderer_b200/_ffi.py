@@ -159,6 +159,9 @@ CORE_SYMBOLS = {
     "hnm_group_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "hnm_dist_unique_id": (C.c_int, [_P]),
     "hnm_dist_init": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32]),
+    "hnm_comm_create": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
+    "hnm_comm_destroy": (None, [_P]),
+    "hnm_dist_attach": (C.c_int, [_P, _P]),
     "hnm_dist_resolve": (C.c_int, [_P, C.c_uint32, _P]),
     "hnm_dist_read_accum": (C.c_int, [_P, _P]),
 }

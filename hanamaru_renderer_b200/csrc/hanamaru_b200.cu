@@ -111,8 +111,15 @@ struct hnm_renderer {
     // and the full image in row order
     double* gathered = nullptr;
     double* full = nullptr;
-    void* nccl_comm = nullptr;     // ncclComm_t of hnm_dist_init
+    void* nccl_comm = nullptr;     // ncclComm_t of hnm_dist_init (owned) or of the attached hnm_comm (borrowed)
+    bool owns_comm = false;
     uint32_t dist_rank = 0, dist_nranks = 0;
+};
+
+struct hnm_comm {
+    void* comm = nullptr;  // ncclComm_t
+    int device = 0;
+    uint32_t rank = 0, num_ranks = 0;
 };
 
 struct hnm_group {
@@ -555,7 +562,7 @@ void hnm_renderer_destroy(hnm_renderer* r) {
     if (r->rng_stream) cudaStreamSynchronize(r->rng_stream);
     if (r->stream) cudaStreamSynchronize(r->stream);
     r->timer.collect();
-    if (r->nccl_comm && nccl().ok) nccl().CommDestroy(r->nccl_comm);
+    if (r->nccl_comm && r->owns_comm && nccl().ok) nccl().CommDestroy(r->nccl_comm);
     for (auto p : r->allocs) cudaFree(p);
     if (r->rgb8_host) cudaFreeHost(r->rgb8_host);
     for (auto e : r->marks) if (e) cudaEventDestroy(e);
@@ -1075,7 +1082,38 @@ int hnm_dist_init(hnm_renderer* r, const uint8_t* id, uint32_t rank, uint32_t nu
     NcclApi::UniqueId u;
     memcpy(u.internal, id, HNM_DIST_ID_BYTES);
     HNM_NCCL(nccl().CommInitRank(&r->nccl_comm, (int)num_ranks, u, (int)rank));
+    r->owns_comm = true;
     r->dist_rank = rank; r->dist_nranks = num_ranks;
+    return ensure_gather_buffers(r);
+}
+int hnm_comm_create(int device, const uint8_t* id, uint32_t rank, uint32_t num_ranks, hnm_comm** out) {
+    if (!id || !out) return set_error(HNM_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (num_ranks == 0 || rank >= num_ranks) return set_error(HNM_ERR_INVALID, "bad rank / num_ranks");
+    if (!nccl().ok) return set_error(HNM_ERR_STATE, "NCCL unavailable: " + nccl().why);
+    HNM_CUDA(cudaSetDevice(device));
+    NcclApi::UniqueId u;
+    memcpy(u.internal, id, HNM_DIST_ID_BYTES);
+    void* c = nullptr;
+    HNM_NCCL(nccl().CommInitRank(&c, (int)num_ranks, u, (int)rank));
+    hnm_comm* h = new hnm_comm();
+    h->comm = c; h->device = device; h->rank = rank; h->num_ranks = num_ranks;
+    *out = h;
+    return 0;
+}
+void hnm_comm_destroy(hnm_comm* comm) {
+    if (!comm) return;
+    if (comm->comm && nccl().ok) { cudaSetDevice(comm->device); nccl().CommDestroy(comm->comm); }
+    delete comm;
+}
+int hnm_dist_attach(hnm_renderer* r, hnm_comm* comm) {
+    if (!r || !comm) return set_error(HNM_ERR_INVALID, "null argument");
+    if (comm->rank != r->P.rank || comm->num_ranks != r->P.nranks) return set_error(HNM_ERR_INVALID, "the communicator's rank / size differ from the renderer's shard");
+    if (comm->device != r->scene->device) return set_error(HNM_ERR_INVALID, "the communicator belongs to another device");
+    if (r->nccl_comm) return set_error(HNM_ERR_STATE, "the renderer already has a communicator");
+    r->nccl_comm = comm->comm;
+    r->owns_comm = false;
+    r->dist_rank = comm->rank; r->dist_nranks = comm->num_ranks;
     return ensure_gather_buffers(r);
 }
 static int dist_gather(hnm_renderer* r) {

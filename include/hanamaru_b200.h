@@ -324,6 +324,15 @@ int hnm_group_get_counters(hnm_group* g, hnm_counters* out); /* summed over the 
 #define HNM_DIST_ID_BYTES 128u
 int hnm_dist_unique_id(uint8_t* id);
 int hnm_dist_init(hnm_renderer* r, const uint8_t* id, uint32_t rank, uint32_t num_ranks);
+/* A communicator that outlives renderers: the reference's `render` is called once per
+ * image (src/main.rs:1216) and a renderer lives for one call, but ncclCommInitRank
+ * costs seconds at 8 ranks.  A host process creates ONE hnm_comm after its
+ * rendezvous and attaches it to every renderer it makes (instead of
+ * hnm_dist_init); the renderer uses it and does not destroy it. */
+typedef struct hnm_comm hnm_comm;
+int hnm_comm_create(int device, const uint8_t* id, uint32_t rank, uint32_t num_ranks, hnm_comm** out);
+void hnm_comm_destroy(hnm_comm* comm);
+int hnm_dist_attach(hnm_renderer* r, hnm_comm* comm);
 /* Collective (every rank calls it, same order).  rgb8 == NULL: take part in
  * the gather only, asynchronously.  rgb8 != NULL: also run `update_imgbuf`
  * on the gathered image and return it (host, width*height*3). */

@@ -94,6 +94,19 @@ ctx.dist_init(ids[0], rank, world)
 ctx.render_passes(1, passes)
 img = ctx.dist_resolve(passes, want_image=(rank == 0))
 acc = ctx.dist_read_accum(want=(rank == 0))
+# a process-lifetime communicator (hnm_comm_create) shared by two renderers in turn (hnm_dist_attach)
+ids2 = [hr.dist_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(ids2, 0)
+comm = hr.DistComm(local, ids2[0], rank, world)
+for k in range(2):
+    c2 = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING, shard=(rank, world, 4))
+    c2.dist_attach(comm)
+    c2.render_passes(1, passes)
+    img2 = c2.dist_resolve(passes, want_image=(rank == 0))
+    if rank == 0 and not np.array_equal(img2, img):
+        print("ATTACH_MISMATCH")
+    c2.close()
+comm.close()
 if rank == 0:
     one = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING)
     one.render_passes(1, passes); one.synchronize()
@@ -111,4 +124,4 @@ def test_dist_nccl_allgather_inside_the_abi(hr, core, tmp_path):
     script.write_text(_WORKER % {"root": ROOT})
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29531", str(script)], capture_output=True, text=True, timeout=600)
-    assert "DIST_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "DIST_OK" in out.stdout and "ATTACH_MISMATCH" not in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -282,6 +282,11 @@ def test_pathtracing_config1_bit_exact(hr, core, oracle, get_scene, get_device_s
     ("rtcamp6_v2_pl", 160, 90, 1, 2),           # 105 StdRng-placed spheres, FIVE emitters (5 shadow rays per NEE), no floor
     ("rtcamp6_v3", 160, 90, 1, 2),              # second emitter: a 1 mm sphere behind the camera, smaller than the NEE window
     ("rtcamp6_v1_pl", 160, 90, 1, 2),           # refractive mesh in front of the light, textured albedo AND roughness floor
+    ("rtcamp6_v4", 160, 90, 1, 2),              # Ryfjallet cube map (the reference's JPEG files, decoded by the C++ host)
+    ("rtcamp5", 160, 90, 1, 2),                 # the same builders under their OWN cube maps (LancellottiChapel), not the
+    ("tbf3", 160, 90, 1, 2),                    # Powerlines stand-in of the `_pl` variants
+    ("rtcamp6_v2", 160, 90, 1, 2),
+    ("rtcamp6_v1", 160, 90, 1, 2),
     ("rtcamp6", 97, 61, 3, 2),                  # odd sizes
     ("rtcamp6", 1, 1, 1, 1),
     ("rtcamp6", 3, 200, 1, 1),                  # W < H: min(res) picks the width
