@@ -92,7 +92,7 @@ d=json.loads(sys.stdin.read()); print('$prec config $c', round(d['value'],1), 'm
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/prof_trace3_$RND python tools/traffic_probe.py bvh_heavy 1920 1080 > $OUT/p2.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirm_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p3.log 2>&1
              HNM_CONFIRM_TMA=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirmtma_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p4.log 2>&1
-             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen -c 1 -f -o gpurun_out/prof_isaac_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p5.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen_tm -c 1 -f -o gpurun_out/prof_isaac_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p5.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade_surf -c 2 -f -o gpurun_out/prof_shade_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p6.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nee_resolve -c 1 -f -o gpurun_out/prof_neer_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p7.log 2>&1
              ls -la gpurun_out/*$RND* ;;
