@@ -353,8 +353,8 @@ def run_ours(args):
                         "algorithmic_bytes_per_unit": b, "units_per_launch": units / nl,
                         "segments_per_sample": seg / max(1, paths_p), "shadow_rays_per_sample": sh / max(1, paths_p),
                         "note": "not HBM bound by construction: the scene is L2 resident and HBM only carries the wavefront records; "
-                                "ISAAC-64 seeding is ALU-latency bound at 112 paths (224 KB of shared-memory state) per SM, "
-                                "k_trace is issue bound (profiles/)"}
+                                "ISAAC-64 seeding is bound by the dependent integer chains of two warps per scheduler (112 states in shared "
+                                "memory, 112 more in tensor memory per SM), k_trace is issue bound (profiles/ncu_r02.md)"}
 
     # ---- end-to-end through the C ABI, host buffers, wall clock ----------------------------------------------
     # (the device-timed renderer is released first: a second 25 GB arena next to a live one makes cudaMalloc 4x slower)

@@ -93,6 +93,7 @@ struct hnm_renderer {
     // Sliced generation (HNM_RNG_SLICES=k, default 4; 0 = one launch released after bounce HNM_RNG_START_BOUNCE): the generation of the next batch runs as k stoppable launches of
     // k_isaac_raygen_tm, one beside the confirm / shade kernels of each of the first k bounces -- never beside k_trace,
     // which competes with it for the same issue slots and integer pipe -- and one last launch that finishes the set.
+    int shade_threads = 256;         // HNM_SHADE_THREADS=128: CTAs of the shade / resolve kernels (finer grain beside a generation slice)
     int rng_slices = 4;
     uint32_t* gen_stop = nullptr;    // device word: stop level (k_gen_stop raises it, a slice of level <= it winds down)
     uint32_t gen_epoch = 0;          // level of the last stoppable slice
@@ -276,9 +277,10 @@ void launch_nee_resolve(hnm_renderer* r, int bounce) {
     RParams& P = r->P;
     cudaStream_t st = r->stream;
     CandLists cand = r->cand;
-    if (r->trace_stats) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<true, false><<<grid, 256, 0, st>>>(P, cand, bounce); });
-    else if (r->fast_math) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, true><<<grid, 256, 0, st>>>(P, cand, bounce); });
-    else launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, false><<<grid, 256, 0, st>>>(P, cand, bounce); });
+    const int T = r->shade_threads, G = grid * (256 / T);
+    if (r->trace_stats) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<true, false><<<G, T, 0, st>>>(P, cand, bounce); });
+    else if (r->fast_math) launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, true><<<G, T, 0, st>>>(P, cand, bounce); });
+    else launch_timed(r, "nee_resolve", [&] { k_nee_resolve<false, false><<<G, T, 0, st>>>(P, cand, bounce); });
 }
 
 // k_trace over one or two ray lists; k_confirm for the FIRST list if `confirm_first` (a shadow-ray list is confirmed by
@@ -402,6 +404,7 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             if (want_prefetch && r->rng_start_bounce <= 0) { int rc = prefetch_next(); if (rc) return rc; }
         }
         bind_gen_set(P, g);
+        const int ST = r->shade_threads, SG = grid * (256 / ST);
         launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
         for (int b = 1; b <= last; b++) {
             if (b == 1) select_first_bounce(r, g);
@@ -419,13 +422,13 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
                 launch_trace(r, trace_name(r, b), &cam, nullptr, &P.counters[b * C_STRIDE + C_WORK], S_SEGMENTS, true, mid);
             }
             if (r->fast_math) {
-                launch_timed(r, "shade_miss", [&] { k_shade_miss<true><<<grid, 256, 0, st>>>(P, b); });
-                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, true><<<grid, 256, 0, st>>>(P, b); });
-                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, true><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_miss", [&] { k_shade_miss<true><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, true><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, true><<<SG, ST, 0, st>>>(P, b); });
             } else {
-                launch_timed(r, "shade_miss", [&] { k_shade_miss<false><<<grid, 256, 0, st>>>(P, b); });
-                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<grid, 256, 0, st>>>(P, b); });
-                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<grid, 256, 0, st>>>(P, b); });
+                launch_timed(r, "shade_miss", [&] { k_shade_miss<false><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<SG, ST, 0, st>>>(P, b); });
             }
             if (slice_here) {
                 // ... and winds down when this bounce's shade kernels are done; the next trace waits for it
@@ -610,6 +613,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
     if (const char* e = getenv("HNM_ISAAC_TMEM")) r->isaac_tmem = atoi(e) != 0;
+    if (const char* e = getenv("HNM_SHADE_THREADS")) { int t = atoi(e); if (t == 64 || t == 128 || t == 256) r->shade_threads = t; }
     if (const char* e = getenv("HNM_RNG_SLICES")) r->rng_slices = std::max(0, std::min(8, atoi(e)));
     if (const char* e = getenv("HNM_ISAAC_ROUNDS")) r->isaac_rounds = std::max(0, atoi(e));
     if (const char* e = getenv("HNM_TRACE_BLOCKS")) { int k = atoi(e); if (k >= 1 && k <= 16) r->trace_blocks_per_sm = k; }

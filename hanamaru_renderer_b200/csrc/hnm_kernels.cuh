@@ -181,6 +181,13 @@ __device__ __forceinline__ void isaac64_init(uint64_t* mem, uint64_t s0, uint64_
 // Shared-memory accesses of the round are volatile PTX with compile-time offsets from a row register: their ORDER in the
 // instruction stream is the order written here (ptxas would otherwise sink the static-index loads next to their uses,
 // which a single in-order warp then waits for).
+// ~(a ^ b) as one LOP3 per half (ptxas emitted the xor and the not separately)
+HNM_D uint64_t xnor64(uint64_t a, uint64_t b) {
+    uint32_t lo, hi;
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(lo) : "r"((uint32_t)a), "r"((uint32_t)b));
+    asm("lop3.b32 %0, %1, %2, 0, 0xC3;" : "=r"(hi) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)));
+    return (uint64_t)lo | ((uint64_t)hi << 32);
+}
 template <int OFF>
 HNM_D uint64_t lds64v(uint32_t saddr) {
     uint64_t v;
@@ -251,7 +258,7 @@ __device__ __forceinline__ void isaac64_round(uint64_t* mem, Sink sink) {
     ISAAC_STEP(aa ^ (aa >> 5), row, base, 0, 3, 2 + (HALF), SINK)                                           \
     ISAAC_STEP(aa ^ (aa << 12), row, base, 1, 4, 3 + (HALF), SINK)                                          \
     ISAAC_STEP(aa ^ (aa >> 33), row, base, 2, 5, 4 + (HALF), SINK)                                          \
-    ISAAC_STEP(~(aa ^ (aa << 21)), row, base, 3, 6, 5 + (HALF), SINK)
+    ISAAC_STEP(xnor64(aa, aa << 21), row, base, 3, 6, 5 + (HALF), SINK)
 #define ISAAC_NOSINK(i, v)
     // only the last KEEP outputs (rsl[256-KEEP .. 255], the first KEEP words of the stream) are handed to `sink`
 #define ISAAC_SINK(i, v) if ((i) >= 256 - KEEP) sink(i, v)
@@ -262,7 +269,7 @@ __device__ __forceinline__ void isaac64_round(uint64_t* mem, Sink sink) {
     ISAAC_STEP(aa ^ (aa >> 5), row, 124, 0, 3, 130, ISAAC_NOSINK)
     ISAAC_STEP(aa ^ (aa << 12), row, 124, 1, 4, 131, ISAAC_NOSINK)
     ISAAC_STEP(aa ^ (aa >> 33), row, 124, 2, 5, -124, ISAAC_NOSINK)
-    ISAAC_STEP(~(aa ^ (aa << 21)), row, 124, 3, 6, -123, ISAAC_NOSINK)
+    ISAAC_STEP(xnor64(aa, aa << 21), row, 124, 3, 6, -123, ISAAC_NOSINK)
     row += 4 * ROW;
 #pragma unroll 1
     for (int base = 128; base < 256 - KEEP; base += 4, row += 4 * ROW) { ISAAC_4STEPS(row, base, -128, ISAAC_NOSINK) }
@@ -272,7 +279,7 @@ __device__ __forceinline__ void isaac64_round(uint64_t* mem, Sink sink) {
     ISAAC_STEP(aa ^ (aa >> 5), row, 252, 0, 3, -126, ISAAC_SINK)
     ISAAC_STEP(aa ^ (aa << 12), row, 252, 1, 3, -125, ISAAC_SINK)
     ISAAC_STEP(aa ^ (aa >> 33), row, 252, 2, 3, -125, ISAAC_SINK)
-    ISAAC_STEP(~(aa ^ (aa << 21)), row, 252, 3, 3, -125, ISAAC_SINK)
+    ISAAC_STEP(xnor64(aa, aa << 21), row, 252, 3, 3, -125, ISAAC_SINK)
     sink(255, ldy + xs);
 #undef ISAAC_SINK
 #undef ISAAC_NOSINK

@@ -45,6 +45,14 @@ def test_isaac64_known_answers_on_device(hr, core, oracle):
     got = hr.isaac64_batch(seeds, 32)
     want = np.stack([oracle.isaac64(s, 32) for s in seeds])
     assert np.array_equal(got, want)
+    # group sizes around the 28-path granule of the TMEM pipeline, partial tails, fewer groups than warp pairs, and a
+    # count that covers several groups per pair (20000 > 148 SMs x 4 pairs x 28)
+    for n in (1, 27, 28, 29, 113):
+        assert np.array_equal(hr.isaac64_batch(seeds[:n], 32), want[:n]), n
+    big = rng.integers(0, 2 ** 63, size=(20000, 4), dtype=np.uint64)
+    gb = hr.isaac64_batch(big, 5)
+    for k in (0, 1, 27, 28, 16575, 16576, 19999):
+        assert np.array_equal(gb[k], oracle.isaac64(big[k], 5)), k
     got = hr.isaac64_batch(seeds[:200], 700)  # > 256 outputs: refill
     want = np.stack([oracle.isaac64(s, 700) for s in seeds[:200]])
     assert np.array_equal(got, want)

@@ -136,6 +136,17 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/sl1.log 2>&1; cat $OUT/sl1.log ;;
     sl2)     { for e in "HNM_RNG_SLICES=5 HNM_PROFILE_OVERLAP=1" "HNM_RNG_SLICES=0 HNM_PROFILE_OVERLAP=1" "HNM_RNG_OVERLAP=0"; do echo "== $e"; env $e timeout 200 python tools/time_passes.py rtcamp6 1920 1080 12 2>&1 | tail -2; done; } > $OUT/sl2.log 2>&1; cat $OUT/sl2.log ;;
+    bt1)     { for b in 3 4 6 8; do
+                 echo "== batch $b"
+                 for c in 2 4; do timeout 300 python bench.py --config $c --steps 4 --batch $b --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/bt1.log 2>&1; cat $OUT/bt1.log ;;
+    sh1)     { timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_SHADE_THREADS=128 timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -1 | cut -c1-100
+               for e in "HNM_X=1" "HNM_SHADE_THREADS=128" "HNM_SHADE_THREADS=64"; do
+                 echo "== $e"
+                 for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3), {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items()})"; done; done; } > $OUT/sh1.log 2>&1; cat $OUT/sh1.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
