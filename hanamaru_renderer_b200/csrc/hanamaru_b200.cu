@@ -63,6 +63,7 @@ struct hnm_renderer {
     bool isaac_tmem = true;        // generation through the TMEM pipeline (k_isaac_raygen_tm); HNM_ISAAC_TMEM=0: k_isaac_raygen
     int isaac_rounds = 0;          // HNM_ISAAC_ROUNDS=k: generation CTAs of k rounds (k x 112 paths) instead of one persistent CTA per SM
     bool confirm_tma = false;      // HNM_CONFIRM_TMA=1: the TMA-staged k_confirm (A/B)
+    bool confirm_pairs = true;     // k_confirm_pairs ((ray, candidate) pairs spread over the lanes); HNM_CONFIRM_PAIRS=0: one ray per lane
     bool fast_math = false;        // hnm_set_precision(HNM_PRECISION_FAST_MATH): opt-in, statistical parity only
     bool rng_midtrace = false;     // HNM_RNG_MIDTRACE=1: the prefetch is enqueued right behind a trace launch, without waiting for it
     uint64_t launches = 0;
@@ -308,11 +309,13 @@ void launch_trace(hnm_renderer* r, const char* name, const TraceJob* j0, const T
     C.njobs = 1;
     if (r->trace_stats) {
         launch_timed(r, name, [&] { k_trace<true><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
-        if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, C); });
+        if (confirm_first && r->confirm_pairs) launch_timed(r, "confirm", [&] { k_confirm_pairs<true><<<cgrid, 256, 0, st>>>(sc, C); });
+        else if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<true><<<cgrid, 256, 0, st>>>(sc, C); });
     } else {
         launch_timed(r, name, [&] { k_trace<false><<<grid, TRACE_THREADS, 0, st>>>(sc, A); });
         if (prefetch_behind_trace && r->prefetch_hook) r->prefetch_hook();
         if (confirm_first && r->confirm_tma) launch_timed(r, "confirm", [&] { k_confirm_tma<false><<<r->sm_count * HNM_CONFIRM_MIN_BLOCKS, 256, 0, st>>>(sc, C); });
+        else if (confirm_first && r->confirm_pairs) launch_timed(r, "confirm", [&] { k_confirm_pairs<false><<<cgrid, 256, 0, st>>>(sc, C); });
         else if (confirm_first) launch_timed(r, "confirm", [&] { k_confirm<false><<<cgrid, 256, 0, st>>>(sc, C); });
     }
 }
@@ -612,6 +615,7 @@ int hnm_renderer_create(hnm_scene* scene, const hnm_camera* camera, uint32_t wid
     if (const char* e = getenv("HNM_RNG_MIDTRACE")) r->rng_midtrace = atoi(e) != 0;
     if (const char* e = getenv("HNM_PROFILE_OVERLAP")) r->profile_overlap = atoi(e) != 0;
     if (const char* e = getenv("HNM_CONFIRM_TMA")) r->confirm_tma = atoi(e) != 0;
+    if (const char* e = getenv("HNM_CONFIRM_PAIRS")) r->confirm_pairs = atoi(e) != 0;
     if (const char* e = getenv("HNM_ISAAC_TMEM")) r->isaac_tmem = atoi(e) != 0;
     if (const char* e = getenv("HNM_SHADE_THREADS")) { int t = atoi(e); if (t == 64 || t == 128 || t == 256) r->shade_threads = t; }
     if (const char* e = getenv("HNM_RNG_SLICES")) r->rng_slices = std::max(0, std::min(8, atoi(e)));

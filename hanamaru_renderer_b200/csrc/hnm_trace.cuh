@@ -47,7 +47,11 @@ namespace hnm {
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_REFILL = HNM_TRACE_REFILL;  // refetch when fewer lanes than this are still traversing
 
-constexpr int TRACE_CAND = 8;                    // candidate-list capacity per ray
+#ifndef HNM_TRACE_CAND
+#define HNM_TRACE_CAND 32
+#endif
+constexpr int TRACE_CAND = HNM_TRACE_CAND;       // candidate-list capacity per ray (<= 32: k_confirm_pairs keeps a bit per entry)
+static_assert(TRACE_CAND >= 1 && TRACE_CAND <= 32, "candidate-list capacity");
 constexpr uint32_t CAND_OVERFLOW = 0xFFFFFFFFu;  // list overflowed: k_confirm runs the exact traversal
 constexpr uint32_t CAND_OCCLUDED = 0xFFFFFFFEu;  // bounded query ended early: report "no hit"
 // candidate id: kind (LEAF_TRI / LEAF_SPHERE / LEAF_CUBOID) << 30 | triangle index (reference leaf order) or element id
@@ -201,6 +205,101 @@ HNM_D bool sphere_pretest(const float4* __restrict__ ef, const RayF& R, float& b
     *t_lo = tl;
     if (disc - Ed > 0.0f && tl > 0.0f && R.t0 == 0.0f) best_ub = fminf(best_ub, th * 1.000001f + 1e-30f);
     return true;
+}
+
+// The exact fallback for one ray: hnm_device.cuh's trace() with two additions.  (1) Every leaf triangle first takes the f32
+// pre-test above and only the survivors the f64 test: a ray that overflows its candidate list grazes dense geometry, and
+// trace() ran ~190 f64 triangle tests for it (ncu, 75 k-triangle scene: the single lane doing that set the duration of every
+// k_confirm launch, ~1 ms each whatever the ray count).  (2) `ub_cull` -- the bound k_trace had reached when it gave up --
+// culls nodes and triangles from the start (the listed path culls with the same bound: `lo > ub`).  The pre-test's own
+// "certain hit" tightening is NOT used (a copy of the bound is passed): rays with infinite reciprocals come here precisely
+// because a geometrically certain hit may be one the reference's box chain never reaches; only confirmed hits tighten.
+template <bool STATS>
+HNM_D Hit trace_pretested(const DScene& sc, D3 o, D3 dir, float ub_cull, TraceStats* st) {
+    Hit best;
+    best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
+    double t0 = 0.0;
+    float fmaxo = fmaxf(fmaxf(fabsf((float)o.x), fabsf((float)o.y)), fabsf((float)o.z));
+    if (fmaxo > sc.far_limit) {
+        double dist;
+        bool h = aabb_intersect_ray(sc.bounds_lo[0], sc.bounds_lo[1], sc.bounds_lo[2], sc.bounds_hi[0], sc.bounds_hi[1], sc.bounds_hi[2], o, dir, &dist);
+        if (!h) return best;
+        if (dist > 0.0 && dist < sc.inf) t0 = dist * (1.0 - 1e-6);
+    }
+    RayF R;
+    R.ox = (float)(o.x + dir.x * t0); R.oy = (float)(o.y + dir.y * t0); R.oz = (float)(o.z + dir.z * t0);
+    R.ix = (float)(1.0 / dir.x); R.iy = (float)(1.0 / dir.y); R.iz = (float)(1.0 / dir.z);
+    R.rx = (float)(-dir.x); R.ry = (float)(-dir.y); R.rz = (float)(-dir.z);
+    R.t0 = __double2float_ru(t0);
+    R.K = (fmaxf(fmaxf(fabsf(R.ox), fabsf(R.oy)), fabsf(R.oz)) + sc.scene_r) * 4.76837158203125e-07f;  // as in k_trace
+#if HNM_TRACE_FMA_SLABS
+    R.nx = R.ny = R.nz = R.fx = R.fy = R.fz = 0.f;  // (the slab tests below use the subtract form)
+#endif
+    const float W = 4.76837158203125e-07f;  // 2^-21: covers the rounding of (lo-o)*inv in f32
+    int32_t stack[HNM_STACK];
+    int sp = 0;
+    int32_t cur = 0;
+    for (;;) {
+        // distances are measured from the advanced origin; a confirmed hit or k_trace's bound culls
+        const float bestf = fminf(__double2float_ru(best.t - t0), ub_cull);
+        if (cur >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + cur);
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+            if (STATS) st->nodes++;
+            float a0 = (n0.x - R.ox) * R.ix, b0 = (n0.w - R.ox) * R.ix;
+            float a1 = (n0.y - R.oy) * R.iy, b1 = (n1.x - R.oy) * R.iy;
+            float a2 = (n0.z - R.oz) * R.iz, b2 = (n1.y - R.oz) * R.iz;
+            float tmin0 = fmaxf(fmaxf(fminf(a0, b0), fminf(a1, b1)), fminf(a2, b2));
+            float tmax0 = fminf(fminf(fmaxf(a0, b0), fmaxf(a1, b1)), fmaxf(a2, b2));
+            float c0 = (n1.z - R.ox) * R.ix, e0 = (n2.y - R.ox) * R.ix;
+            float c1 = (n1.w - R.oy) * R.iy, e1 = (n2.z - R.oy) * R.iy;
+            float c2 = (n2.x - R.oz) * R.iz, e2 = (n2.w - R.oz) * R.iz;
+            float tmin1 = fmaxf(fmaxf(fminf(c0, e0), fminf(c1, e1)), fminf(c2, e2));
+            float tmax1 = fminf(fminf(fmaxf(c0, e0), fmaxf(c1, e1)), fmaxf(c2, e2));
+            float lo0 = tmin0 - fabsf(tmin0) * W, up0 = tmax0 + fabsf(tmax0) * W;
+            float lo1 = tmin1 - fabsf(tmin1) * W, up1 = tmax1 + fabsf(tmax1) * W;
+            bool h0 = (lo0 <= up0) && (up0 >= 0.0f) && (lo0 <= bestf);
+            bool h1 = (lo1 <= up1) && (up1 >= 0.0f) && (lo1 <= bestf);
+            if (h0 && h1) {
+                bool swap = lo1 < lo0;
+                int32_t nearc = swap ? n3.y : n3.x;
+                int32_t farc = swap ? n3.x : n3.y;
+                if (sp < HNM_STACK) stack[sp++] = farc;
+                cur = nearc;
+                continue;
+            } else if (h0) {
+                cur = n3.x;
+                continue;
+            } else if (h1) {
+                cur = n3.y;
+                continue;
+            }
+        } else {
+            int kind = leaf_kind(cur);
+            uint32_t first = leaf_first(cur);
+            if (kind == LEAF_TRI) {
+                uint32_t cnt = leaf_count(cur);
+                for (uint32_t k = 0; k < cnt; k++) {
+                    float ubc = fminf(__double2float_ru(best.t - t0), ub_cull), tlo;
+                    if (!tri_pretest(sc.trif + 3 * (size_t)(first + k), R, ubc, &tlo)) continue;  // the exact test cannot accept it
+                    uint32_t g = __ldg(sc.tri_perm + first + k);
+                    DTri tr = load_tri(sc.tris + g);
+                    if (STATS) st->prims++;
+                    tri_test(sc, tr, g, o, dir, best);
+                }
+            } else if (kind == LEAF_SPHERE) {
+                if (STATS) st->prims++;
+                sphere_test(sc, sc.elements[first], first, sc.elements, o, dir, best);
+            } else if (kind == LEAF_CUBOID) {
+                if (STATS) st->prims++;
+                cuboid_test(sc, sc.elements[first], first, sc.elements, o, dir, best);
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+    return best;
 }
 
 // `cur` of a lane without a ray: a LEAF_NONE link, so that "holds a node" is cur >= 0 and "holds a leaf" is
@@ -449,7 +548,7 @@ HNM_D Hit confirm_ray(const DScene& sc, const CandLists& cand, uint32_t slot, ui
     best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
     if (n == CAND_OVERFLOW) {
         TraceStats st{0, 0};
-        best = trace<STATS>(sc, o, dir, &st);
+        best = trace_pretested<STATS>(sc, o, dir, ub, &st);
         if (STATS) n_prims += st.prims;
     } else if (n != CAND_OCCLUDED) {
         for (uint32_t k = 0; k < n; k++) {
@@ -548,6 +647,157 @@ __global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm(DScene 
     }
     if (STATS) {
         for (int s = 16; s > 0; s >>= 1) n_prims += __shfl_xor_sync(0xFFFFFFFFu, n_prims, s);
+        if (lane == 0) atomicAdd(&A.stats[A.stat_prims], (unsigned long long)n_prims);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ k_confirm, pair-parallel
+// k_confirm gives every lane its own ray and walks that ray's list: 45 % of the camera rays have no candidate at all and a
+// few have several, so the heavy part -- the f64 triangle test and the reference's box chain, ~400 instructions behind
+// three dependent loads -- ran at 4-8 of 32 lanes, once per list POSITION (ncu, 75 k-triangle scene: 8.7 lanes per
+// instruction, 11.6 long-scoreboard stall cycles per issued instruction).  Here the (ray, candidate) PAIRS of a warp's 32
+// rays are spread over the lanes: a prefix sum of the per-ray counts numbers the pairs, lane j of a round takes pair j (binary
+// search for its owner over the prefix sums, five shuffles), loads that ray and that candidate itself, runs the SAME exact
+// test into a private Hit, and the owners pull their pairs' results back with shuffles and keep the best.  The closest hit is
+// order independent by construction (argmin t, ties by the reference's DFS order: `better`), so the result is the one
+// confirm_ray computes.  32 rays are now one round of dependent loads instead of max-list-length rounds.
+HNM_D bool hit_better(const DScene& sc, const Hit& h, const Hit& best) {
+    if (h.kind == LEAF_NONE) return false;
+    if (best.kind == LEAF_NONE) return true;
+    if (h.t < best.t) return true;
+    if (h.t > best.t) return false;
+    // exact tie (tri_test / sphere_test / cuboid_test): a triangle beats an element, the later triangle beats the earlier, the
+    // earlier element (top-level DFS order) beats the later
+    if (h.kind == LEAF_TRI) return best.kind != LEAF_TRI || h.id > best.id;
+    if (best.kind == LEAF_TRI) return false;
+    return sc.elements[h.id].seq < sc.elements[best.id].seq;
+}
+template <bool STATS>
+__global__ void __launch_bounds__(256, HNM_CONFIRM_MIN_BLOCKS) k_confirm_pairs(DScene sc, TraceArgs A) {
+    const int lane = threadIdx.x & 31;
+    const TraceJob& J = A.job[0];
+    const uint32_t n0 = *J.count;
+    uint32_t n_prims = 0;
+    const bool classify = J.q_miss != nullptr;
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (;;) {
+        uint32_t wbase = 0;
+        if (lane == 0) wbase = atomicAdd(A.work_confirm, 32u);
+        wbase = __shfl_sync(FULL, wbase, 0);
+        if (wbase >= n0) break;
+        const uint32_t idx = wbase + lane;
+        const bool have = idx < n0;
+        const uint32_t slot = J.slot0 + idx;
+        // ---- this lane's ray: header and the list positions that survive the final bound
+        uint32_t n = 0;
+        float ub = 0.f;
+        if (have) { n = __ldcs(A.cand.n + slot); ub = __ldcs(A.cand.ub + slot); }
+        const bool overflow = have && n == CAND_OVERFLOW;
+        if (STATS && overflow) atomicAdd(&A.stats[6], 1ull);  // S_OVERFLOW
+        const uint32_t listed = (have && n != CAND_OVERFLOW && n != CAND_OCCLUDED) ? n : 0u;
+        uint32_t vm = 0;
+        const uint32_t maxl = __reduce_max_sync(FULL, listed);
+        for (uint32_t k = 0; k < maxl; k++)
+            if (k < listed) {
+                const float lo = __ldcs(A.cand.lo + (size_t)k * A.cand.stride + slot);
+                if (!(lo > ub)) vm |= 1u << k;  // (culled after it was listed otherwise)
+            }
+        const uint32_t cnt = __popc(vm);
+        uint32_t end = cnt;  // inclusive prefix sum
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, end, s);
+            if (lane >= s) end += v;
+        }
+        const uint32_t off = end - cnt;
+        const uint32_t T = __shfl_sync(FULL, end, 31);
+        const uint32_t maxc = __reduce_max_sync(FULL, cnt);
+        if (STATS) n_prims += cnt;
+        Hit best;
+        best.t = sc.inf; best.u = 0.0; best.v = 0.0; best.kind = LEAF_NONE; best.id = 0;
+        for (uint32_t j0 = 0; j0 < T; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            // owner of pair j: the first lane whose inclusive prefix exceeds j
+            int a = 0, b = 31;
+#pragma unroll
+            for (int it = 0; it < 5; it++) {
+                const int mid = (a + b) >> 1;
+                const uint32_t e = __shfl_sync(FULL, end, mid);
+                if (e > j) b = mid; else a = mid + 1;
+            }
+            const int L = a & 31;
+            const uint32_t offL = __shfl_sync(FULL, off, L), vmL = __shfl_sync(FULL, vm, L);
+            Hit h;
+            h.t = sc.inf; h.u = 0.0; h.v = 0.0; h.kind = LEAF_NONE; h.id = 0;
+            if (j < T) {
+                const uint32_t k = __fns(vmL, 0, (int)(j - offL) + 1);  // list position of this pair
+                const uint32_t q = wbase + (uint32_t)L;
+                const uint32_t cid = __ldcs(A.cand.id + (size_t)k * A.cand.stride + (J.slot0 + q));
+                const D3 o = d3(J.ray[0][q], J.ray[1][q], J.ray[2][q]);
+                const D3 dir = d3(J.ray[3][q], J.ray[4][q], J.ray[5][q]);
+                const uint32_t kind = cid >> 30, id = cid & 0x3FFFFFFFu;
+                if (kind == LEAF_TRI) {
+                    DTri tr = load_tri(sc.tris + id);
+                    tri_test(sc, tr, id, o, dir, h);
+                } else if (kind == LEAF_SPHERE) {
+                    sphere_test(sc, sc.elements[id], id, sc.elements, o, dir, h);
+                } else {
+                    cuboid_test(sc, sc.elements[id], id, sc.elements, o, dir, h);
+                }
+            }
+            // the owners pull the results of their pairs of this round
+            for (uint32_t r = 0; r < maxc; r++) {
+                const int src = (int)(off + r) - (int)j0;
+                Hit g;
+                g.t = __shfl_sync(FULL, h.t, src & 31);
+                g.u = __shfl_sync(FULL, h.u, src & 31);
+                g.v = __shfl_sync(FULL, h.v, src & 31);
+                g.kind = __shfl_sync(FULL, h.kind, src & 31);
+                g.id = __shfl_sync(FULL, h.id, src & 31);
+                if (r < cnt && src >= 0 && src < 32 && hit_better(sc, g, best)) best = g;
+            }
+        }
+        int cls = -1;
+        if (have) {
+            if (overflow) {
+                // the list overflowed (or the ray must not be culled in f32 at all): plain exact traversal
+                const D3 o = d3(__ldcs(J.ray[0] + idx), __ldcs(J.ray[1] + idx), __ldcs(J.ray[2] + idx));
+                const D3 dir = d3(__ldcs(J.ray[3] + idx), __ldcs(J.ray[4] + idx), __ldcs(J.ray[5] + idx));
+                TraceStats st{0, 0};
+                best = trace_pretested<STATS>(sc, o, dir, ub, &st);
+                if (STATS) n_prims += st.prims;
+            }
+            __stcs(J.hit_t + idx, best.t); __stcs(J.hit_u + idx, best.u); __stcs(J.hit_v + idx, best.v);
+            __stcs(J.hit_id + idx, make_uint2(best.kind, best.id));
+            if (classify) {
+                if (best.kind == LEAF_NONE) cls = 0;
+                else {
+                    uint32_t el = best.kind == LEAF_TRI ? sc.tri_elem[best.id] : best.id;
+                    int surface = sc.materials[sc.elements[el].material].surface;
+                    cls = nee_available(surface) ? 2 : 1;
+                }
+            }
+        }
+        if (classify) {
+            // three queues, ONE round trip: lanes 0..2 each reserve the warp's slots in one queue at the same time
+            const unsigned m0 = __ballot_sync(FULL, cls == 0), m1 = __ballot_sync(FULL, cls == 1), m2 = __ballot_sync(FULL, cls == 2);
+            uint32_t base = 0;
+            if (lane < 3) {
+                const unsigned m = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+                uint32_t* ctr = lane == 0 ? J.cnt_miss : (lane == 1 ? J.cnt_delta : J.cnt_nee);
+                if (m) base = atomicAdd(ctr, (uint32_t)__popc(m));
+            }
+            const uint32_t b0 = __shfl_sync(FULL, base, 0), b1 = __shfl_sync(FULL, base, 1), b2 = __shfl_sync(FULL, base, 2);
+            if (cls >= 0) {
+                const unsigned m = cls == 0 ? m0 : (cls == 1 ? m1 : m2);
+                uint32_t* qq = cls == 0 ? J.q_miss : (cls == 1 ? J.q_delta : J.q_nee);
+                qq[(cls == 0 ? b0 : (cls == 1 ? b1 : b2)) + __popc(m & ((1u << lane) - 1u))] = idx;
+            }
+        }
+    }
+    if (STATS) {
+        for (int s = 16; s > 0; s >>= 1) n_prims += __shfl_xor_sync(FULL, n_prims, s);
         if (lane == 0) atomicAdd(&A.stats[A.stat_prims], (unsigned long long)n_prims);
     }
 }

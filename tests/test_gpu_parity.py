@@ -192,13 +192,13 @@ def test_exact_ties_follow_reference_order(hr, core, oracle, assets):
 
 
 def test_candidate_list_overflow_falls_back_to_exact_traversal(hr, core, oracle, assets):
-    """k_trace keeps at most 8 candidates per ray; a ray with more (here: 24 coincident copies of every triangle, all
-    tied at the same distance) is re-traced by k_confirm with the plain exact traversal.  Same bits either way, for
+    """k_trace keeps at most 32 candidates per ray; a ray with more (here: 40 coincident copies of every triangle, all
+    tied at the same distance) is re-traced by k_confirm with the exact traversal (trace_pretested).  Same bits either way, for
     single rays and for whole paths (NEE shadow rays through the stack included)."""
     rng = np.random.default_rng(11)
     v = np.array([[-2, 0.5, -2], [2, 0.5, -2], [2, 0.5, 2], [-2, 0.5, 2], [0, 1.5, 0]], np.float64)
     f = np.array([[0, 1, 2], [0, 2, 3], [0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.uint32)
-    f = np.concatenate([f] * 24)
+    f = np.concatenate([f] * 40)
     b = hr.SceneBuilder(assets)
     b.camera((0, 3, 6), (0, 0.5, 0), aperture=0.05, focus_distance=6.0)
     b.add_mesh(v, f, hr.SceneBuilder.material(hr.SURFACE_GGX, param=0.8, roughness=0.3, albedo=(0.8, 0.6, 0.4)))
@@ -214,7 +214,7 @@ def test_candidate_list_overflow_falls_back_to_exact_traversal(hr, core, oracle,
     got, want = dev.intersect(o, d), oracle.intersect(scene, o, d)
     for fld in got.dtype.names:
         assert field_equal(got[fld], want[fld]), fld
-    assert (got["element"] == 0).mean() > 0.3          # many rays do hit the 24-fold mesh
+    assert (got["element"] == 0).mean() > 0.3          # many rays do hit the 40-fold mesh
     ctx = render_gpu(hr, dev, scene, 96, 54, hr.MODE_PATHTRACING, 1, 2)
     acc, cnt = oracle.render(scene, 96, 54, hr.MODE_PATHTRACING, 1, 2)
     assert np.array_equal(bits(ctx.read_accum()), bits(acc))

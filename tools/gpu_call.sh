@@ -147,6 +147,14 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
                  for c in 2 4; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3), {k: round(v/d['detail']['profiled_passes'],3) for k,v in d['detail']['kernel_ms'].items()})"; done; done; } > $OUT/sh1.log 2>&1; cat $OUT/sh1.log ;;
+    cf1)     { timeout 200 python tools/setup_time.py 2>&1 | tail -2
+               HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirm3 python tools/traffic_probe.py bvh_heavy 1920 1080 2>&1 | tail -1
+               HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_nee_resolve -c 1 -f -o gpurun_out/prof_neer3 python tools/traffic_probe.py bvh_heavy 1920 1080 2>&1 | tail -1; } > $OUT/cf1.log 2>&1; cat $OUT/cf1.log ;;
+    cp1)     { timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "scenes_bit_exact or config1 or overflow or ties or full_size" 2>&1 | tail -3
+               for sc in rtcamp6 bvh_heavy diamond; do for e in 0 1; do echo "== $sc HNM_CONFIRM_PAIRS=$e"; HNM_CONFIRM_PAIRS=$e HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 6 2>&1 | tail -1 | cut -c1-200; done; done; } > $OUT/cp1.log 2>&1; cat $OUT/cp1.log ;;
+    cp2)     { HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm_pairs -c 3 -f -o gpurun_out/prof_cpairs3 python tools/traffic_probe.py bvh_heavy 1920 1080 2>&1 | tail -1
+               HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py bvh_heavy 1920 1080 3 2>&1 | tail -2; } > $OUT/cp2.log 2>&1; cat $OUT/cp2.log ;;
+    cp3)     { for lib in "" _variants/cand16.so _variants/cand32.so; do for sc in bvh_heavy rtcamp6; do echo "== $sc lib=$lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py $sc 160 90 1 2 2>&1 | tail -1 | cut -c1-90; HNM_CORE_LIB=$lib HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 3 2>&1 | tail -2; done; done; } > $OUT/cp3.log 2>&1; cat $OUT/cp3.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
