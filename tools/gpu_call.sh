@@ -90,7 +90,7 @@ d=json.loads(sys.stdin.read()); print('$prec config $c', round(d['value'],1), 'm
              export HNM_RNG_OVERLAP=0
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/prof_trace_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p1.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_trace -c 2 -f -o gpurun_out/prof_trace3_$RND python tools/traffic_probe.py bvh_heavy 1920 1080 > $OUT/p2.log 2>&1
-             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirm_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p3.log 2>&1
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm_pairs -c 2 -f -o gpurun_out/prof_confirm_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p3.log 2>&1
              HNM_CONFIRM_TMA=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm -c 2 -f -o gpurun_out/prof_confirmtma_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p4.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_isaac_raygen_tm -c 1 -f -o gpurun_out/prof_isaac_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p5.log 2>&1
              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade_surf -c 2 -f -o gpurun_out/prof_shade_$RND python tools/traffic_probe.py rtcamp6 1920 1080 > $OUT/p6.log 2>&1
@@ -155,6 +155,7 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
     cp2)     { HNM_RNG_OVERLAP=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_confirm_pairs -c 3 -f -o gpurun_out/prof_cpairs3 python tools/traffic_probe.py bvh_heavy 1920 1080 2>&1 | tail -1
                HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py bvh_heavy 1920 1080 3 2>&1 | tail -2; } > $OUT/cp2.log 2>&1; cat $OUT/cp2.log ;;
     cp3)     { for lib in "" _variants/cand16.so _variants/cand32.so; do for sc in bvh_heavy rtcamp6; do echo "== $sc lib=$lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py $sc 160 90 1 2 2>&1 | tail -1 | cut -c1-90; HNM_CORE_LIB=$lib HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 3 2>&1 | tail -2; done; done; } > $OUT/cp3.log 2>&1; cat $OUT/cp3.log ;;
+    sah1)    { for e in "HNM_X=1" "HNM_SAH_MAXLEAF=4" "HNM_SAH_MAXLEAF=12" "HNM_SAH_CT=0.5" "HNM_SAH_CT=2.0" "HNM_SAH_CT=0.5 HNM_SAH_MAXLEAF=4" "HNM_SAH_CT=2.0 HNM_SAH_MAXLEAF=12"; do for sc in bvh_heavy; do echo "== $sc $e"; env $e HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 3 2>&1 | tail -2 | cut -c1-230; done; done; } > $OUT/sah1.log 2>&1; cat $OUT/sah1.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
