@@ -243,6 +243,10 @@ def test_no_cpu_fallback_without_device(hr):
         hr.DeviceScene(scene, 0)
     with pytest.raises(hr.HanamaruError):
         hr.isaac64_batch([[1, 2, 3, 4]], 8)
+    with pytest.raises(hr.HanamaruError):
+        hr.DistComm(0, bytes(128), 0, 2)   # no device (or no NCCL): an error, not a silent single-rank mode
+    with pytest.raises(hr.HanamaruError):
+        hr.DistComm(0, bytes(128), 3, 2)   # rank >= num_ranks
     # and the product package never imports the oracle
     for root, _, files in os.walk(os.path.join(ROOT, "hanamaru_renderer_b200")):
         for f in files:

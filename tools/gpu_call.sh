@@ -156,6 +156,9 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
                HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py bvh_heavy 1920 1080 3 2>&1 | tail -2; } > $OUT/cp2.log 2>&1; cat $OUT/cp2.log ;;
     cp3)     { for lib in "" _variants/cand16.so _variants/cand32.so; do for sc in bvh_heavy rtcamp6; do echo "== $sc lib=$lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py $sc 160 90 1 2 2>&1 | tail -1 | cut -c1-90; HNM_CORE_LIB=$lib HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 3 2>&1 | tail -2; done; done; } > $OUT/cp3.log 2>&1; cat $OUT/cp3.log ;;
     sah1)    { for e in "HNM_X=1" "HNM_SAH_MAXLEAF=4" "HNM_SAH_MAXLEAF=12" "HNM_SAH_CT=0.5" "HNM_SAH_CT=2.0" "HNM_SAH_CT=0.5 HNM_SAH_MAXLEAF=4" "HNM_SAH_CT=2.0 HNM_SAH_MAXLEAF=12"; do for sc in bvh_heavy; do echo "== $sc $e"; env $e HNM_TRACE_STATS=1 HNM_RNG_OVERLAP=0 timeout 300 python tools/time_passes.py $sc 1920 1080 3 2>&1 | tail -2 | cut -c1-230; done; done; } > $OUT/sah1.log 2>&1; cat $OUT/sah1.log ;;
+    c1a)     { for e in "HNM_X=1" "HNM_RNG_SLICES=0" "HNM_RNG_SLICES=1" "HNM_RNG_OVERLAP=0"; do echo "== $e"; env $e timeout 300 python bench.py --config 1 --steps 64 --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config 1', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms/step', round(d['ms_per_step'],3))"; done; } > $OUT/c1a.log 2>&1; cat $OUT/c1a.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
