@@ -346,9 +346,13 @@ HNM_D uint64_t u64_of(uint32_t lo, uint32_t hi) { return (uint64_t)lo | ((uint64
 // TMEM columns [c0, c1) of this warp's lanes -> words [c0 / 2, c1 / 2) of shared-memory column `mem` (stride T words).  Loads of
 // 32 columns, the next one in flight while the 16 words of the current one are stored (with one x16 load at a time the
 // loop was bound by the TMEM load latency: 0.93 -> 0.5 ms of the 7 ms kernel).  All 32 lanes must call.
+#ifndef HNM_TM_COPY_X32
+#define HNM_TM_COPY_X32 0
+#endif
 template <int T>
 HNM_D void tm_copy_to_column(uint32_t tbase, uint64_t* mem, bool active, uint32_t c0, uint32_t c1) {
     if (c0 >= c1) return;
+#if HNM_TM_COPY_X32
     uint32_t c[32];
     tm_ld32(tbase + c0, c);
 #pragma unroll 1
@@ -365,8 +369,31 @@ HNM_D void tm_copy_to_column(uint32_t tbase, uint64_t* mem, bool active, uint32_
         }
     }
     tm_wait_ld();
+#else
+    // two 16-column loads in flight, stored straight from their registers: the same one wait per 32 columns as the x32
+    // form, without its 16-word staging copy (87 -> 64 registers for the whole kernel: the shade kernels beside a
+    // generation slice get a third CTA per SM)
+    uint32_t a[16], b[16];
+    tm_ld16(tbase + c0, a);
+    tm_ld16(tbase + c0 + 16, b);
+#pragma unroll 1
+    for (uint32_t col = c0; col < c1; col += 32) {
+        tm_wait_ld();
+        uint64_t* o = mem + (size_t)(col >> 1) * T;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[j * T] = u64_of(a[2 * j], a[2 * j + 1]);
+        }
+        tm_ld16(tbase + (col + 32 < c1 ? col + 32 : c0), a);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) o[(8 + j) * T] = u64_of(b[2 * j], b[2 * j + 1]);
+        }
+        tm_ld16(tbase + (col + 48 < c1 ? col + 48 : c0), b);
+    }
+    tm_wait_ld();
+#endif
 }
-
 // Work is handed out per warp PAIR, 28 consecutive paths at a time: fetch() is called by the producer warp (every lane gets the
 // same answer) and returns the first path of the next group or ISAAC_NONE; seed(p, s0..s3) is called by the producer lanes
 // for path p = group + lane; sink(p, i, v) and done(p) by the consumer lanes (`done` runs while the state of the next group is

@@ -159,6 +159,11 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
     c1a)     { for e in "HNM_X=1" "HNM_RNG_SLICES=0" "HNM_RNG_SLICES=1" "HNM_RNG_OVERLAP=0"; do echo "== $e"; env $e timeout 300 python bench.py --config 1 --steps 64 --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config 1', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), 'ms/step', round(d['ms_per_step'],3))"; done; } > $OUT/c1a.log 2>&1; cat $OUT/c1a.log ;;
+    cx1)     { timeout 200 python tools/diag_scene.py rtcamp6 160 90 1 2 2>&1 | tail -1 | cut -c1-100
+               for lib in "" _variants/tmx32.so; do echo "== lib=$lib"; HNM_CORE_LIB=$lib HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-60
+                 for c in 2 4; do HNM_CORE_LIB=$lib timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/cx1.log 2>&1; cat $OUT/cx1.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
