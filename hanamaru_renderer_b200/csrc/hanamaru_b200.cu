@@ -371,7 +371,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
         int hook_rc = 0;
         // ---- sliced prefetch: stoppable generation launches beside the confirm / shade kernels of the first bounces
         hnm_renderer::GenSet& o = r->gen[s ^ 1];
-        const bool sliced = want_prefetch && r->isaac_tmem && r->rng_slices > 0 &&
+        // (the stop level is a 32-bit counter that only grows; 0xFFFFFFFF means "never stop": slicing simply ends long before)
+        const bool sliced = want_prefetch && r->isaac_tmem && r->rng_slices > 0 && r->gen_epoch < 0xFFFFFF00u &&
                             !(o.valid && o.sampling_first == next_first && o.batch == next_batch);
         RParams G;
         uint32_t slice_epoch = 0;
