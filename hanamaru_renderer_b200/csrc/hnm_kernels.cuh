@@ -805,6 +805,25 @@ HNM_D uint32_t queue_alloc_grouped(bool pred, uint32_t key, uint32_t* counter) {
     __syncthreads();
     return pred ? s_gbase + s_base[k] + woff + rank : 0u;
 }
+// The same grouping inside ONE warp's run of slots: no shared memory, no CTA barrier (A/B: HNM_SHADE_OCTANT_SORT=2).
+HNM_D uint32_t queue_alloc_warp_grouped(bool pred, uint32_t key, uint32_t* counter) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const unsigned all = __ballot_sync(FULL, pred);
+    if (all == 0) return 0;
+    uint32_t before = 0, mine = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 8; k++) {
+        const unsigned m = __ballot_sync(FULL, pred && key == k);
+        if (k < key) before += __popc(m);
+        if (k == key) mine = __popc(m & ((1u << lane) - 1u));
+    }
+    const int leader = __ffs(all) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(all));
+    base = __shfl_sync(FULL, base, leader);
+    return base + before + mine;
+}
 HNM_D uint32_t direction_octant(D3 d) { return (signbit_(d.x) ? 1u : 0u) | (signbit_(d.y) ? 2u : 0u) | (signbit_(d.z) ? 4u : 0u); }
 
 HNM_D D3 load_ray_o(const RParams& P, uint32_t q) { return d3(P.rin[0][q], P.rin[1][q], P.rin[2][q]); }
@@ -933,7 +952,9 @@ __global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParam
             }
             // None: `break` before the emission is added (src/renderer.rs:190-193)
         }
-#if HNM_SHADE_OCTANT_SORT
+#if HNM_SHADE_OCTANT_SORT == 2
+        uint32_t q2 = queue_alloc_warp_grouped(alive, direction_octant(nd), &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
+#elif HNM_SHADE_OCTANT_SORT
         uint32_t q2 = queue_alloc_grouped(alive, direction_octant(nd), &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
 #else
         uint32_t q2 = queue_alloc(alive, &P.counters[(bounce + 1) * C_STRIDE + C_RAY]);
