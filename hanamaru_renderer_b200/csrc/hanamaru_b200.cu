@@ -409,6 +409,8 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
         }
         bind_gen_set(P, g);
         const int ST = r->shade_threads, SG = grid * (256 / ST);
+        // k_shade_surf: its CTA is the domain of the octant grouping
+        const int SUT = (HNM_SURF_THREADS > 256) ? HNM_SURF_THREADS : ST, SUG = (HNM_SURF_THREADS > 256) ? grid * 256 / HNM_SURF_THREADS : SG;
         launch_timed(r, "batch_begin", [&] { k_batch_begin<<<1, 1, 0, st>>>(P); });
         for (int b = 1; b <= last; b++) {
             if (b == 1) select_first_bounce(r, g);
@@ -427,12 +429,12 @@ int run_batch(hnm_renderer* r, uint32_t sampling_first, uint32_t batch, uint32_t
             }
             if (r->fast_math) {
                 launch_timed(r, "shade_miss", [&] { k_shade_miss<true><<<SG, ST, 0, st>>>(P, b); });
-                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, true><<<SG, ST, 0, st>>>(P, b); });
-                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, true><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, true><<<SUG, SUT, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, true><<<SUG, SUT, 0, st>>>(P, b); });
             } else {
                 launch_timed(r, "shade_miss", [&] { k_shade_miss<false><<<SG, ST, 0, st>>>(P, b); });
-                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<SG, ST, 0, st>>>(P, b); });
-                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<SG, ST, 0, st>>>(P, b); });
+                launch_timed(r, "shade_delta", [&] { k_shade_surf<false, false><<<SUG, SUT, 0, st>>>(P, b); });
+                launch_timed(r, "shade_nee", [&] { k_shade_surf<true, false><<<SUG, SUT, 0, st>>>(P, b); });
             }
             if (slice_here) {
                 // ... and winds down when this bounce's shade kernels are done; the next trace waits for it

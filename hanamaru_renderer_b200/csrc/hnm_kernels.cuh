@@ -880,7 +880,10 @@ __global__ void __launch_bounds__(256, HNM_MISS_MIN_BLOCKS) k_shade_miss(RParams
 #define HNM_SHADE_MIN_BLOCKS 4  /* 64 registers (spills to local memory): measured best of 2 / 3 / 4 / 5 / 6 */
 #endif
 template <bool NEE, bool FAST>
-__global__ void __launch_bounds__(256, HNM_SHADE_MIN_BLOCKS) k_shade_surf(RParams P, int bounce) {
+#ifndef HNM_SURF_THREADS
+#define HNM_SURF_THREADS 256  /* CTA size of k_shade_surf = the domain of the octant grouping (A/B: 512 with 2 CTAs/SM) */
+#endif
+__global__ void __launch_bounds__(HNM_SURF_THREADS, HNM_SHADE_MIN_BLOCKS * 256 / HNM_SURF_THREADS) k_shade_surf(RParams P, int bounce) {
     const int cls = NEE ? C_NEE : C_DELTA;
     note_warp_slot(P.dbg, 2);
     const uint32_t n = P.counters[bounce * C_STRIDE + cls];

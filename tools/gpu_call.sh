@@ -166,7 +166,7 @@ import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/cx1.log 2>&1; cat $OUT/cx1.log ;;
     final)   { timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
                timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_run.py 2>&1 | grep -v "^$" | tail -6; } > $OUT/final.log 2>&1; cat $OUT/final.log ;;
-    so1)     { for lib in "" _variants/sort0.so _variants/sort2.so; do echo "== lib=$lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_CORE_LIB=$lib HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-200
+    so1)     { for lib in ${SO_LIBS:-"" _variants/sort0.so _variants/sort2.so}; do echo "== lib=$lib"; HNM_CORE_LIB=$lib timeout 200 python tools/diag_scene.py rtcamp5_pl 160 90 1 2 2>&1 | tail -1 | cut -c1-100; HNM_CORE_LIB=$lib HNM_RNG_OVERLAP=0 timeout 200 python tools/time_passes.py rtcamp6 1920 1080 3 2>&1 | tail -1 | cut -c1-200
                  for c in 2 4; do HNM_CORE_LIB=$lib timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/so1.log 2>&1; cat $OUT/so1.log ;;
