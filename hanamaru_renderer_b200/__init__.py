@@ -309,6 +309,17 @@ class RenderContext:
         _check(_ffi.core().hnm_resolve(self._h, C.c_void_p(accum_full_device) if accum_full_device else None, sampling, _vp(out)))
         return out
 
+    def resolve_begin(self, sampling, accum_full_device=None):
+        """First half of resolve(): enqueued behind the passes submitted so far, returns at once."""
+        _check(_ffi.core().hnm_resolve_begin(self._h, C.c_void_p(accum_full_device) if accum_full_device else None, sampling))
+
+    def resolve_end(self, out=None):
+        """Second half: waits for the image of the matching resolve_begin / dist_resolve_begin."""
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.uint8)
+        _check(_ffi.core().hnm_resolve_end(self._h, _vp(out)))
+        return out
+
     def deinterleave(self, gathered_device, full_device):
         _check(_ffi.core().hnm_deinterleave(self._h, C.c_void_p(gathered_device), C.c_void_p(full_device)))
 
@@ -360,6 +371,10 @@ class RenderContext:
         """Use a process-lifetime communicator (DistComm) instead of creating one for this renderer."""
         _check(_ffi.core().hnm_dist_attach(self._h, comm._h))
         self._comm = comm  # keep it alive
+
+    def dist_resolve_begin(self, sampling, want_image=True):
+        """Collective, asynchronous: gather (+ update_imgbuf on the ranks that want the image; collect it with resolve_end)."""
+        _check(_ffi.core().hnm_dist_resolve_begin(self._h, sampling, 1 if want_image else 0))
 
     def dist_resolve(self, sampling, out=None, want_image=True):
         """Collective.  Ranks with want_image=False only take part in the gather (asynchronously) and return None."""

@@ -10,6 +10,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CORE_LIB = os.environ.get("HNM_CORE_LIB") or os.path.join(HERE, "libhanamaru_b200.so")  # override: tuning experiments only
 HOST_LIB = os.path.join(HERE, "libhanamaru_host.so")
 
+
+def _point_at_the_bundled_nccl():
+    """In a Python process torch loads the libnccl.so.2 of the nvidia-nccl wheel; the core binds NCCL with dlopen at its first
+    hnm_dist_* / hnm_comm_* call.  Two different libnccl.so.2 in one process clash by soname, so the core is told to load the
+    same file (HNM_NCCL_LIB, read by the C side; a Rust host simply links or sets its own).  No import of torch here."""
+    if os.environ.get("HNM_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["HNM_NCCL_LIB"] = cand
+                return
+    except Exception:
+        pass
+
+
+_point_at_the_bundled_nccl()
+
 HNM_ABI_VERSION = 1
 HNM_RNG_TAIL = 32
 
@@ -130,6 +151,8 @@ CORE_SYMBOLS = {
     "hnm_read_accum": (C.c_int, [_P, _P]),
     "hnm_accum_device_ptr": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_size_t)]),
     "hnm_resolve": (C.c_int, [_P, _P, C.c_uint32, _P]),
+    "hnm_resolve_begin": (C.c_int, [_P, _P, C.c_uint32]),
+    "hnm_resolve_end": (C.c_int, [_P, _P]),
     "hnm_deinterleave": (C.c_int, [_P, _P, _P]),
     "hnm_get_counters": (C.c_int, [_P, C.POINTER(Counters)]),
     "hnm_get_kernel_times": (C.c_int, [_P, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
@@ -162,6 +185,7 @@ CORE_SYMBOLS = {
     "hnm_comm_create": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint32, C.POINTER(_P)]),
     "hnm_comm_destroy": (None, [_P]),
     "hnm_dist_attach": (C.c_int, [_P, _P]),
+    "hnm_dist_resolve_begin": (C.c_int, [_P, C.c_uint32, C.c_int]),
     "hnm_dist_resolve": (C.c_int, [_P, C.c_uint32, _P]),
     "hnm_dist_read_accum": (C.c_int, [_P, _P]),
 }

@@ -113,6 +113,8 @@ struct hnm_renderer {
     // and the full image in row order
     double* gathered = nullptr;
     double* full = nullptr;
+    cudaEvent_t resolve_done = nullptr;  // hnm_resolve_begin / hnm_resolve_end
+    bool resolve_pending = false;
     void* nccl_comm = nullptr;     // ncclComm_t of hnm_dist_init (owned) or of the attached hnm_comm (borrowed)
     bool owns_comm = false;
     uint32_t dist_rank = 0, dist_nranks = 0;
@@ -530,8 +532,13 @@ NcclApi& nccl() {
     static NcclApi api;
     static std::once_flag once;
     std::call_once(once, [] {
+        // Order: the file HNM_NCCL_LIB names (the Python mirror points it at the wheel torch itself loads, so that both
+        // agree whichever comes first: two different libnccl.so.2 in one process clash by soname); an instance the process
+        // has already loaded; the system's.
         void* h = nullptr;
-        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (const char* e = getenv("HNM_NCCL_LIB")) { if (*e) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL); }
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+        if (!h) for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
         if (!h) { api.why = "libnccl.so.2 not found"; return; }
         api.GetUniqueId = (int (*)(NcclApi::UniqueId*))dlsym(h, "ncclGetUniqueId");
         api.CommInitRank = (int (*)(void**, int, NcclApi::UniqueId, int))dlsym(h, "ncclCommInitRank");
@@ -580,6 +587,7 @@ void hnm_renderer_destroy(hnm_renderer* r) {
         if (g.released) cudaEventDestroy(g.released);
     }
     if (r->rng_gate) cudaEventDestroy(r->rng_gate);
+    if (r->resolve_done) cudaEventDestroy(r->resolve_done);
     for (int k = 0; k < 8; k++) { if (r->slice_open[k]) cudaEventDestroy(r->slice_open[k]); if (r->slice_done[k]) cudaEventDestroy(r->slice_done[k]); }
     if (r->rng_stream) cudaStreamDestroy(r->rng_stream);
     if (r->stream) cudaStreamDestroy(r->stream);
@@ -877,6 +885,35 @@ int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t samplin
     return 0;
 }
 
+// The same resolve in two halves, so that a host can enqueue the NEXT passes before it waits for this image
+// (`report_progress` every interval, src/renderer.rs:216-226: the image of step i is read while step i + 1 runs).
+static int resolve_mark(hnm_renderer* r) {
+    if (!r->resolve_done && cudaEventCreateWithFlags(&r->resolve_done, cudaEventDisableTiming) != cudaSuccess)
+        return set_error(HNM_ERR_CUDA, "cudaEventCreate failed");
+    HNM_CUDA(cudaEventRecord(r->resolve_done, r->stream));
+    r->resolve_pending = true;
+    return 0;
+}
+int hnm_resolve_begin(hnm_renderer* r, const void* accum_full_device, uint32_t sampling) {
+    if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
+    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
+    if (!accum_full_device && r->P.nranks != 1) return set_error(HNM_ERR_STATE, "a sharded renderer needs the gathered full-image buffer");
+    if (r->resolve_pending) return set_error(HNM_ERR_STATE, "hnm_resolve_begin: the previous image has not been collected (hnm_resolve_end)");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    int rc = enqueue_resolve(r, accum_full_device, sampling);
+    if (rc) return rc;
+    return resolve_mark(r);
+}
+int hnm_resolve_end(hnm_renderer* r, uint8_t* rgb8) {
+    if (!r || !rgb8) return set_error(HNM_ERR_INVALID, "null argument");
+    if (!r->resolve_pending) return set_error(HNM_ERR_STATE, "hnm_resolve_end without hnm_resolve_begin");
+    HNM_CUDA(cudaSetDevice(r->scene->device));
+    HNM_CUDA(cudaEventSynchronize(r->resolve_done));
+    r->resolve_pending = false;
+    memcpy(rgb8, r->rgb8_host, (size_t)r->P.W * r->P.H * 3);
+    return 0;
+}
+
 int hnm_get_counters(hnm_renderer* r, hnm_counters* out) {
     if (!r || !out) return set_error(HNM_ERR_INVALID, "null argument");
     HNM_CUDA(cudaSetDevice(r->scene->device));
@@ -1101,8 +1138,8 @@ int hnm_comm_create(int device, const uint8_t* id, uint32_t rank, uint32_t num_r
     if (!id || !out) return set_error(HNM_ERR_INVALID, "null argument");
     *out = nullptr;
     if (num_ranks == 0 || rank >= num_ranks) return set_error(HNM_ERR_INVALID, "bad rank / num_ranks");
+    HNM_CUDA(cudaSetDevice(device));  // (before NCCL is bound: a host without a device never loads it)
     if (!nccl().ok) return set_error(HNM_ERR_STATE, "NCCL unavailable: " + nccl().why);
-    HNM_CUDA(cudaSetDevice(device));
     NcclApi::UniqueId u;
     memcpy(u.internal, id, HNM_DIST_ID_BYTES);
     void* c = nullptr;
@@ -1147,6 +1184,16 @@ int hnm_dist_resolve(hnm_renderer* r, uint32_t sampling, uint8_t* rgb8) {
     HNM_CUDA(cudaStreamSynchronize(r->stream));
     memcpy(rgb8, r->rgb8_host, (size_t)r->P.W * r->P.H * 3);
     return 0;
+}
+// Collective, asynchronous: the gather (and, with want_image != 0, update_imgbuf) is enqueued; hnm_resolve_end collects.
+int hnm_dist_resolve_begin(hnm_renderer* r, uint32_t sampling, int want_image) {
+    if (!r) return set_error(HNM_ERR_INVALID, "null renderer");
+    if (sampling == 0) return set_error(HNM_ERR_STATE, "resolve with sampling == 0");
+    if (want_image && r->resolve_pending) return set_error(HNM_ERR_STATE, "hnm_dist_resolve_begin: the previous image has not been collected (hnm_resolve_end)");
+    int rc = dist_gather(r);
+    if (rc || !want_image) return rc;
+    if ((rc = enqueue_resolve(r, r->full, sampling))) return rc;
+    return resolve_mark(r);
 }
 int hnm_dist_read_accum(hnm_renderer* r, double* rgb) {
     if (!r) return set_error(HNM_ERR_INVALID, "null renderer");

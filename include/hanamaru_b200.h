@@ -255,6 +255,14 @@ int hnm_accum_device_ptr(hnm_renderer* r, void** ptr, size_t* bytes);
  * single-shard renderer pass NULL to use its own buffer).  rgb8 is HOST
  * memory, width*height*3 bytes, row 0 = top. */
 int hnm_resolve(hnm_renderer* r, const void* accum_full_device, uint32_t sampling, uint8_t* rgb8);
+/* The same in two halves: _begin enqueues update_imgbuf and the copy into a
+ * pinned buffer behind the passes enqueued so far and returns at once; _end
+ * waits for exactly that work and hands the image out.  A host that reports
+ * progress every interval (src/renderer.rs:216-226) enqueues the next passes
+ * between the two, so the device never waits for the host's copy.  One image
+ * may be pending per renderer. */
+int hnm_resolve_begin(hnm_renderer* r, const void* accum_full_device, uint32_t sampling);
+int hnm_resolve_end(hnm_renderer* r, uint8_t* rgb8);
 /* Scatter gathered per-rank shards ([num_ranks][owned_rows*width*3] f64 on
  * the device) into image row order. */
 int hnm_deinterleave(hnm_renderer* r, const void* gathered_device, void* full_device);
@@ -337,6 +345,10 @@ int hnm_dist_attach(hnm_renderer* r, hnm_comm* comm);
  * the gather only, asynchronously.  rgb8 != NULL: also run `update_imgbuf`
  * on the gathered image and return it (host, width*height*3). */
 int hnm_dist_resolve(hnm_renderer* r, uint32_t sampling, uint8_t* rgb8);
+/* Collective and asynchronous: the gather is enqueued on every rank; a rank
+ * with want_image != 0 also enqueues update_imgbuf and collects the image
+ * later with hnm_resolve_end. */
+int hnm_dist_resolve_begin(hnm_renderer* r, uint32_t sampling, int want_image);
 /* Collective; rgb != NULL receives the gathered f64 buffer in image row order. */
 int hnm_dist_read_accum(hnm_renderer* r, double* rgb);
 

@@ -381,6 +381,30 @@ def test_deinterleave_and_resolve_on_device(hr, core, oracle, get_scene, get_dev
         c.close()
 
 
+def test_resolve_in_two_halves(hr, core, get_scene, get_device_scene):
+    """hnm_resolve_begin / hnm_resolve_end: the image enqueued behind step i is the image resolve() returns for step i, also when the
+    passes of step i + 1 are enqueued before it is collected; misuse is an error."""
+    scene, dev = get_scene("rtcamp6"), get_device_scene("rtcamp6")
+    w, h = 160, 90
+    ctx = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING)
+    ref = hr.RenderContext(dev, scene.camera, w, h, hr.MODE_PATHTRACING)
+    imgs = []
+    for i in range(3):
+        ctx.render_passes(1 + 2 * i, 2)
+        if i > 0:
+            imgs.append(ctx.resolve_end())
+        ctx.resolve_begin(2 * (i + 1))
+        with pytest.raises(hr.HanamaruError):
+            ctx.resolve_begin(2 * (i + 1))      # one image may be pending
+    imgs.append(ctx.resolve_end())
+    with pytest.raises(hr.HanamaruError):
+        ctx.resolve_end()                        # nothing pending
+    for i in range(3):
+        ref.render_passes(1 + 2 * i, 2)
+        assert np.array_equal(ref.resolve(2 * (i + 1)), imgs[i]), i
+    ctx.close(); ref.close()
+
+
 def test_resolve_edge_cases(hr, core, oracle, get_scene, get_device_scene):
     """update_imgbuf on adversarial buffers: NaN, negatives, huge values, tiny images (u32 wrap of the bilateral taps)."""
     import torch

@@ -170,6 +170,10 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
                  for c in 2 4; do HNM_CORE_LIB=$lib timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/so1.log 2>&1; cat $OUT/so1.log ;;
+    e2e1)    { timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "two_halves or resolve" 2>&1 | tail -2
+               timeout 600 python bench.py --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('config 2 value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['e2e']['seconds'])"; } > $OUT/e2e1.log 2>&1; cat $OUT/e2e1.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
