@@ -174,6 +174,9 @@ d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pa
                timeout 600 python bench.py --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('config 2 value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['e2e']['seconds'])"; } > $OUT/e2e1.log 2>&1; cat $OUT/e2e1.log ;;
+    sl3)     { for e in "HNM_RNG_SLICES=4" "HNM_RNG_SLICES=6" "HNM_RNG_SLICES=8"; do echo "== $e"; for c in 2 4 3; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/sl3.log 2>&1; cat $OUT/sl3.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
