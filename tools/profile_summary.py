@@ -61,12 +61,17 @@ def main():
         md += ["## Launch list (`--metrics gpu__time_duration.sum`; cold-cache, serialised: compare SHARES)", "", table, "",
                "total %.3f ms over the captured launches" % T, ""]
     traffic = {}
-    for name, key in (("trace", "trace"), ("confirm", "confirm"), ("isaac", "isaac_raygen"), ("shade", "shade_nee")):
+    titles = {"trace3": "trace3 (k_trace on the 75 k-triangle scene of BASELINE config 3)", "confirmtma": "confirmtma (k_confirm_tma, the TMA A/B)",
+              "neer": "neer (k_nee_resolve)"}
+    for name, key in (("trace", "trace"), ("trace3", None), ("confirm", "confirm"), ("confirmtma", None), ("isaac", "isaac_raygen"),
+                      ("shade", "shade_nee"), ("neer", None)):
         rep = os.path.join(src, "prof_%s_%s.ncu-rep" % (name, rnd))
         if not os.path.exists(rep):
             continue
         table, vals, units, hdr = raw_metrics(rep)
-        md += ["## `--set full` capture: %s" % name, "", table, ""]
+        md += ["## `--set full` capture: %s" % titles.get(name, name), "", table, ""]
+        if key is None:
+            continue
         try:
             def to_bytes(v, u):
                 return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
