@@ -177,6 +177,9 @@ d=json.loads(sys.stdin.read()); print('config 2 value', round(d['value'],1), 'e2
     sl3)     { for e in "HNM_RNG_SLICES=4" "HNM_RNG_SLICES=6" "HNM_RNG_SLICES=8"; do echo "== $e"; for c in 2 4 3; do env $e timeout 300 python bench.py --config $c --steps 4 --no-e2e --no-cpu --no-traffic 2>/dev/null | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('  config $c', round(d['value'],1), 'ms/pass', round(d['ms_per_step']/d['config']['passes_per_step'],3))"; done; done; } > $OUT/sl3.log 2>&1; cat $OUT/sl3.log ;;
+    race2)   { timeout 500 compute-sanitizer --tool racecheck python tools/sanitize_run.py 2>&1 | grep -v "^$" | tail -4
+               timeout 400 compute-sanitizer --tool synccheck python tools/sanitize_run.py 2>&1 | grep -v "^$" | tail -3; } > $OUT/race2.log 2>&1; cat $OUT/race2.log ;;
+    sync2)   { timeout 400 compute-sanitizer --tool synccheck --print-limit 6 python tools/sanitize_run.py 2>&1 | grep -v "^$" | head -60; } > $OUT/sync2.log 2>&1; cat $OUT/sync2.log ;;
     *) echo "unknown step $step" ;;
   esac
 done
